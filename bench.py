@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/s of the RAFT recurrent-inference path (BASELINE.json metric).
+
+Workload (N GPUs, weak scaling): BASELINE config[1] per GPU -- raft-things, 1 frame pair per GPU,
+436x1024 (replicate-padded to 440x1024), 32 iterations, synthetic frames, seeded
+random weights in the reference's npz naming (no network: neither Sintel nor the Drive weights).
+A "step" = one forward pass (encoders + correlation build + 32 x (lookup, update block) + convex
+upsampling) over the batch.
+
+  value  : pairs/s with the frames already resident in HBM (CUDA events, max over ranks)
+  e2e    : pairs/s through the public API (networks.RAFT.RAFT.forward) with PINNED HOST frames:
+           H2D of both frames and D2H of the flow inside the timed region, every step
+  roofline        : the update-block convolutions (dominant: ~97% of hot-path FLOPs), tensor bound
+  roofline_lookup : the correlation-lookup kernel (the metric's namesake), HBM bound
+  cpu_baseline    : the CPU oracle (torch fp32 restatement of the reference; TF is not installable)
+                    timed on the host cores of the same box
+
+--impl reference times that same CPU restatement as the reference arm (oracle/ is executed only
+there and in cpu_baseline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "raft-tf_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H_IMG, W_IMG, ITERS, SMALL = 436, 1024, 32, False
+H_PAD, W_PAD = 440, 1024
+METRIC = "frame-pairs/sec @ 436x1024, 32 iters (raft-things)"
+# algorithmic work per sample: update block MAC/px/iter, lookup bytes/px/iter
+UPDATE_MAC_PER_PX = 2675968
+LOOKUP_BYTES_PER_PX = 2904  # N*[4*((2r+2)^2*4 + (2r+1)^2*4) + 8], r=4, fp32 volume, fp32-equivalent output
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_forward_time(sample_hw, iters, threads):
+    """One oracle forward on `threads` host cores; returns seconds."""
+    from oracle.raft_oracle import RAFTOracle
+    from raft_b200 import synth
+    torch.set_num_threads(threads)
+    h, w = sample_hw
+    params = synth.make_weights(SMALL)
+    l, r = synth.make_batch(1, h, w)
+    m = RAFTOracle(params, small=SMALL, iters=iters)
+    t0 = time.perf_counter()
+    m.forward(torch.from_numpy(l), torch.from_numpy(r))
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's algorithm on the host CPU (oracle port; the TF original cannot be
+    installed here -- no network, no wheels).  Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    full = (H_PAD, W_PAD)
+    t_probe = cpu_forward_time(full, ITERS, cores)  # doubles as the first warm-up
+    total = args.steps + args.warmup
+    if t_probe * total <= 240.0:
+        sample, scale, desc = full, 1.0, f"1 frame pair {H_PAD}x{W_PAD}, {ITERS} iters per step"
+    else:  # bounded sample: centre crop, throughput scaled by the pixel ratio (favours the CPU: the volume is O(N^2))
+        sample = (224, 512)
+        scale = (sample[0] * sample[1]) / float(H_PAD * W_PAD)
+        desc = (f"1 frame pair {sample[0]}x{sample[1]} crop, {ITERS} iters per step; pairs/s scaled by pixel ratio "
+                f"{scale:.3f} to {H_PAD}x{W_PAD}")
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_forward_time(sample, ITERS, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_forward_time(sample, ITERS, cores)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt * scale
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"raft-things B=1 {H_IMG}x{W_IMG} (padded {H_PAD}x{W_PAD}) {ITERS} iters",
+                       "note": "CPU restatement of gonglixue/RAFT-tf (TensorFlow/tensorpack not installable offline)"},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from raft_b200 import capi, synth
+    from networks.RAFT import RAFT
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch_per_gpu
+    params = synth.make_weights(SMALL)
+    model = RAFT((H_IMG, W_IMG, 3), SimpleNamespace(small=SMALL), iters=ITERS, batch=B, device=dev).load(params)
+    l_np, r_np = synth.make_batch(B, H_IMG, W_IMG, seed0=1000 + rank * B)
+    l_host = torch.from_numpy(l_np).pin_memory()
+    r_host = torch.from_numpy(r_np).pin_memory()
+    l_dev, r_dev = l_host.to(dev), r_host.to(dev)
+    out_host = torch.empty(B, H_IMG, W_IMG, 2, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps, L2 flushed between steps (flush excluded from the timed spans); returns seconds (max over ranks)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        t = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+        if world > 1:
+            tt = torch.tensor([t], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t
+
+    def step_resident():
+        model.forward(l_dev, r_dev)
+
+    def step_e2e():
+        flow = model.forward(l_host, r_host)  # H2D of both frames inside
+        out_host.copy_(flow, non_blocking=True)  # D2H of the result
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    eng = model.engine()
+    launches_per_fwd = eng.launches_per_forward()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t_res = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    t_e2e = timed(step_e2e, args.steps)
+
+    # ---- per-kernel rooflines, measured live with CUDA events on the launching stream ----
+    pk = peaks()
+    h, w, s = eng.h, eng.w, int(SMALL)
+    npix = B * h * w
+    lib = capi.lib
+
+    def ev_time(fn, reps=20):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / 1e3)
+        return statistics.median(ts)
+
+    c1 = eng.coords1.clone()
+    t_upd = ev_time(lambda: capi.check(lib.rb_update_step(s, capi.ptr(eng.blob), capi.ptr(eng.ws), capi.ptr(c1), None, None,
+                                                           B, h, w, capi.stream())))
+    t_look = ev_time(lambda: capi.check(lib.rb_update_lookup(s, capi.ptr(eng.ws), capi.ptr(eng.pyramid), capi.ptr(eng.coords1),
+                                                             B, h, w, capi.stream())))
+    upd_flops = 2.0 * npix * UPDATE_MAC_PER_PX
+    look_bytes = float(npix * LOOKUP_BYTES_PER_PX)
+    roof = {"kernel": "rb_update_step (11 conv_tc_kernel launches + flow_conv7)", "bound": "tensor",
+            "achieved": upd_flops / t_upd / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
+            "frac": upd_flops / t_upd / 1e12 / pk["tf"], "traffic": None, "peak_source": pk["src"],
+            "note": "algorithmic fp32-equivalent FLOPs; each product costs 3 fp16 MMAs (hi/lo split), so frac <= 1/3 by design",
+            "us_per_launch_group": t_upd * 1e6}
+    roof_l = {"kernel": "corr_lookup_kernel<4,split>", "bound": "hbm", "achieved": look_bytes / t_look / 1e9,
+              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": None,
+              "peak_source": pk["src"], "us_per_launch": t_look * 1e6}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        tc = cpu_forward_time((H_PAD, W_PAD), ITERS, cores)
+        cpu = {"value": 1.0 / tc, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": f"1 frame pair {H_PAD}x{W_PAD}, {ITERS} iters, torch-CPU fp32 oracle, one timed forward"}
+
+    if rank == 0:
+        pairs = B * world * args.steps
+        in_bytes = int(l_host.numel() * 4 * 2)
+        line = {"metric": METRIC, "value": pairs / t_res, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": f"raft-things B={B}/GPU {H_IMG}x{W_IMG} (padded {H_PAD}x{W_PAD}) {ITERS} iters",
+                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "flushed between steps (256 MiB write)", "weights": "seeded random (synth.make_weights)"},
+                "e2e": {"value": pairs / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
+                        "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": t_e2e / args.steps * 1e3},
+                "gpu_launches": launches_per_fwd * args.steps, "gpu_launches_per_step": launches_per_fwd,
+                "roofline": roof, "roofline_lookup": roof_l, "clocks": clk}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

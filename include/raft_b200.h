@@ -1,0 +1,137 @@
+/*
+ * raft_b200.h -- C ABI of the B200-native RAFT recurrent-inference hot path.
+ *
+ * The reference (gonglixue/RAFT-tf) has NO native/FFI boundary: its hot path is a set of Python
+ * graph-building functions called from RAFT.network_graph (networks/RAFT.py:78-109).  Each entry
+ * point below replaces one of those functions (cited per symbol); the Python mirrors in
+ * raft-tf_b200/networks/ keep the reference's names and signatures and call these through ctypes.
+ *
+ * Conventions
+ *  - every function returns an int status: 0 = RB_OK, negative = error (see enum); nothing throws
+ *    or aborts; rb_last_error() returns a thread-local description of the last failure;
+ *  - every data pointer is a DEVICE pointer to a caller-owned, contiguous buffer unless the
+ *    parameter name ends in _host; tensors are NHWC fp32 exactly like the reference's TF tensors;
+ *  - `stream` is a cudaStream_t passed as void*; calls only ENQUEUE work on it -- no hidden
+ *    synchronisation, no hidden allocation (scratch comes from caller buffers sized by the
+ *    *_bytes queries) -- so every call except rb_update_weights_pack is CUDA-graph capturable;
+ *  - `small` selects raft-small (radius 3, hidden 96, context 64) vs raft-things (4, 128, 128),
+ *    mirroring args.small (networks/RAFT.py:37-40).
+ */
+#ifndef RAFT_B200_H_
+#define RAFT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  RB_OK = 0,
+  RB_ERR_BAD_SHAPE = -1,
+  RB_ERR_BAD_ARG = -2,
+  RB_ERR_UNSUPPORTED = -3,
+  RB_ERR_CUDA = -4,
+  RB_ERR_WORKSPACE = -5
+};
+
+/* Arithmetic back end for the GEMM-shaped ops (corr build, update-block convs).
+ *   RB_MATH_TC    tcgen05 tensor cores, fp16 hi/lo split operands, 3 MMAs per product,
+ *                 fp32 accumulation in TMEM (error ~2^-22 relative per product);
+ *   RB_MATH_SIMT  the same split operands multiplied on the fp32 CUDA cores (bring-up /
+ *                 cross-check path; identical buffers and epilogues). */
+enum { RB_MATH_TC = 0, RB_MATH_SIMT = 1 };
+
+#define RB_NUM_LEVELS 4
+
+int rb_version(void);
+const char* rb_last_error(void);
+/* Select the back end for subsequent calls on this thread (default RB_MATH_TC). */
+int rb_set_math_mode(int mode);
+int rb_get_math_mode(void);
+/* Number of kernels this library has launched on the calling thread since the last reset. */
+long long rb_launch_count(void);
+void rb_launch_count_reset(void);
+
+/* ---- A4: coords_grid(batch, ht, wd)  networks/utils.py:4-11 ----------------------------------
+ * coords[b,y,x,0] = x, coords[b,y,x,1] = y. */
+int rb_coords_grid(float* coords, int B, int h, int w, void* stream);
+
+/* ---- A1: GetCorrPyramid(fmap1, fmap2, num_levels=4)  networks/model_utils.py:199-221 ----------
+ * pyramid layout: level l (dims h_l = h >> l, w_l = w >> l, floor) is a dense fp32 array
+ * [B*h*w, h_l, w_l]; levels are concatenated, level l starting at rb_corr_level_offset(). */
+int rb_corr_pyramid_bytes(int B, int h, int w, size_t* bytes);
+int rb_corr_level_offset(int B, int h, int w, int level, size_t* offset_floats, int* hl, int* wl);
+int rb_corr_workspace_bytes(int B, int h, int w, int C, size_t* bytes);
+int rb_corr_build(const float* fmap1, const float* fmap2, float* pyramid, int B, int h, int w,
+                  int C, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- A2/A3: SampleCorr(corr_pyramid, coords, num_levels=4, radius)  model_utils.py:224-249 ----
+ * with bilinear_sampler / tf_grid_sample semantics of networks/utils.py:39-103 (truncation toward
+ * zero, index clamping, weights from the clamped x1/y1).  out: [B,h,w,4*(2r+1)^2] fp32, channel =
+ * level*(2r+1)^2 + (x_off+r)*(2r+1) + (y_off+r). */
+int rb_corr_lookup(const float* pyramid, const float* coords, float* out, int B, int h, int w,
+                   int radius, void* stream);
+
+/* ---- A3 (general form): bilinear_sampler(img, coords)  networks/utils.py:101-103 ---------------
+ * img [n,H,W,1], coords [n,S,2] (x,y in pixels) -> out [n,S]; tf_grid_sample semantics (:39-99). */
+int rb_bilinear_sample(const float* img, const float* coords, float* out, int n, int H, int W, int S,
+                       void* stream);
+
+/* ---- A14: tensorpack Conv2D(stride 1, padding 'same', use_bias) on fp32 NHWC tensors -----------
+ * x [B,h,w,cin], W_host HWIO [kh,kw,cin,cout] and b_host [cout] (host pointers; b_host nullable),
+ * y [B,h,w,cout] = act(conv(x,W)+b), act = ReLU if relu != 0.  Synchronises the stream once to upload
+ * the packed kernel (stand-alone / test entry; the update block keeps its weights resident). */
+int rb_conv2d_workspace_bytes(int B, int h, int w, int cin, int cout, int kh, int kw, size_t* bytes);
+int rb_conv2d(const float* x, const float* W_host, const float* b_host, float* y, int B, int h, int w,
+              int cin, int cout, int kh, int kw, int relu, void* workspace, size_t workspace_bytes,
+              void* stream);
+
+/* ---- A5-A11: BasicUpdateBlock / SmallUpdateBlock  model_utils.py:110-194 ----------------------
+ * Weights: rb_update_num_convs(small) convolutions in the fixed order given by
+ * rb_update_conv_name(small, i) (reference variable scopes, e.g. "update_block/gru/convz1");
+ * W_host[i] is the HWIO fp32 kernel [kh,kw,cin,cout], b_host[i] the bias [cout] (host pointers,
+ * as loaded from the reference's .npz).  The packed blob is device memory owned by the caller. */
+int rb_update_num_convs(int small);
+const char* rb_update_conv_name(int small, int i);
+int rb_update_conv_shape(int small, int i, int* kh, int* kw, int* cin, int* cout);
+int rb_update_weights_bytes(int small, size_t* bytes);
+int rb_update_weights_pack(int small, const float* const* W_host, const float* const* b_host,
+                           void* blob, size_t blob_bytes, void* stream);
+
+/* Workspace holding the recurrent state (net), the context features (inp) and every per-iteration
+ * activation.  Must be zero-filled by the caller once before first use (cudaMemset). */
+int rb_update_workspace_bytes(int small, int B, int h, int w, size_t* bytes);
+/* net = tanh(cnet[..., :hidden]) and inp = relu(cnet[..., hidden:]) (RAFT.py:85-87) are supplied
+ * already activated: net [B,h,w,hidden], inp [B,h,w,context]. */
+int rb_update_set_state(int small, void* workspace, const float* net, const float* inp, int B,
+                        int h, int w, void* stream);
+int rb_update_get_net(int small, const void* workspace, float* net, int B, int h, int w,
+                      void* stream);
+/* Lookup written straight into the workspace in the layout the first conv consumes (fast path). */
+int rb_update_lookup(int small, void* workspace, const float* pyramid, const float* coords1, int B,
+                     int h, int w, void* stream);
+/* Same slot filled from an fp32 [B,h,w,4*(2r+1)^2] tensor (functional BasicUpdateBlock mirror). */
+int rb_update_set_corr(int small, void* workspace, const float* corr, int B, int h, int w,
+                       void* stream);
+/* One update-block application: flow = coords1 - coords_grid (RAFT.py:95), motion encoder, GRU,
+ * flow head, coords1 += delta (RAFT.py:102).  delta_out (nullable) receives delta_flow [B,h,w,2];
+ * mask_out (nullable) receives 0.25*mask [B,h,w,576] (things only; model_utils.py:180-183). */
+int rb_update_step(int small, const void* weights, void* workspace, float* coords1,
+                   float* delta_out, float* mask_out, int B, int h, int w, void* stream);
+/* ---- A12: the loop of RAFT.network_graph (RAFT.py:91-102): iters x (lookup, update). ---------- */
+int rb_raft_iterate(int small, const void* weights, void* workspace, const float* pyramid,
+                    float* coords1, float* mask_out, int B, int h, int w, int iters, void* stream);
+
+/* ---- A13: RAFT.upsample_flow (RAFT.py:119-134) and upflow8 (utils.py:105-111) ----------------
+ * flow = coords1 - coords_grid is formed inside; out: [B,8h,8w,2]. */
+int rb_upsample_convex(const float* coords1, const float* mask, float* out, int B, int h, int w,
+                       void* stream);
+/* scale = 1.0 reproduces the reference (no x8, utils.py:110); upstream RAFT would pass 8.0. */
+int rb_upflow8(const float* coords1, float* out, int B, int h, int w, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAFT_B200_H_ */

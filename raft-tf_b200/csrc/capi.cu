@@ -1,0 +1,33 @@
+// Library-level entry points: version, thread-local error string, back-end selection, launch counter.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace rb {
+static thread_local char g_err[512] = "";
+static thread_local int g_mode = RB_MATH_TC;
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { ++g_launches; }
+int math_mode() { return g_mode; }
+}  // namespace rb
+
+extern "C" int rb_version(void) { return 100; }
+extern "C" const char* rb_last_error(void) { return rb::g_err; }
+extern "C" int rb_set_math_mode(int mode) {
+  if (mode != RB_MATH_TC && mode != RB_MATH_SIMT) {
+    rb::set_error("rb_set_math_mode: unknown mode %d", mode);
+    return RB_ERR_BAD_ARG;
+  }
+  rb::g_mode = mode;
+  return RB_OK;
+}
+extern "C" int rb_get_math_mode(void) { return rb::g_mode; }
+extern "C" long long rb_launch_count(void) { return rb::g_launches; }
+extern "C" void rb_launch_count_reset(void) { rb::g_launches = 0; }

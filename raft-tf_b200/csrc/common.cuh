@@ -1,0 +1,213 @@
+// Shared declarations for the raft_b200 kernels: status codes, the fp16 hi/lo "split" operand
+// format, the conv launch descriptor and the fused epilogues every conv back end shares.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/raft_b200.h"
+
+namespace rb {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch();
+int math_mode();
+
+#define RB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      rb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return RB_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define RB_CHECK_LAUNCH(name)                                                     \
+  do {                                                                            \
+    rb::count_launch();                                                           \
+    cudaError_t _e = cudaGetLastError();                                          \
+    if (_e != cudaSuccess) {                                                      \
+      rb::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \
+      return RB_ERR_CUDA;                                                         \
+    }                                                                             \
+  } while (0)
+
+#define RB_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      rb::set_error(__VA_ARGS__);     \
+      return code;                    \
+    }                                 \
+  } while (0)
+
+// ---- split operand format ---------------------------------------------------------------------
+// An fp32 value a is carried as two fp16 numbers: hi = fp16(a) and lo = fp16((a - hi) * 2^11).
+// a ~= hi + lo * 2^-11 to ~22 mantissa bits.  A product a*b is evaluated as
+//   hi_a*hi_b + 2^-11 * (hi_a*lo_b + lo_a*hi_b)          (the lo*lo term, 2^-22, is dropped)
+// with both sums accumulated in fp32: three fp16 tensor-core MMAs per product, two accumulators.
+constexpr float kLoScale = 2048.0f;
+constexpr float kLoInv = 1.0f / 2048.0f;
+
+__host__ __device__ inline void split_f32(float a, __half& hi, __half& lo) {
+  hi = __float2half_rn(a);
+  lo = __float2half_rn((a - __half2float(hi)) * kLoScale);
+}
+__host__ __device__ inline float join_f32(__half hi, __half lo) {
+  return __half2float(hi) + __half2float(lo) * kLoInv;
+}
+
+// A split tensor: two fp16 planes with identical [pixel][channel] layout.
+struct SplitPtr {
+  __half* hi;
+  __half* lo;
+};
+
+// ---- conv launch descriptor -------------------------------------------------------------------
+enum Epilogue : int {
+  EPI_ACT = 0,    // y = act(acc+bias) -> split planes d0 (and d1)
+  EPI_ZR = 1,     // c<hidden: z=sigmoid -> f0 ; else r=sigmoid, r*h(f1) -> d0
+  EPI_Q = 2,      // q=tanh ; h=(1-z)h+zq -> f1 and d0
+  EPI_DELTA = 3,  // c<2: coords1(f1)[c] += v ; optional copy to f2
+  EPI_F32 = 4     // f0[pix*cout+c] = scale*v
+};
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1 };
+
+struct ConvParams {
+  // input activation (split planes), `in_stride` channels per pixel, first channel at in_choff
+  const __half* in_hi;
+  const __half* in_lo;
+  int in_stride, in_choff;
+  int cin_pad;  // channels consumed per tap (multiple of 64)
+  // packed weights [cout_pad][kh*kw][cin_pad] (K-major) as split planes + fp32 bias
+  const __half* w_hi;
+  const __half* w_lo;
+  const float* bias;
+  int cout, cout_pad, kh, kw;
+  int w_per_batch;  // 1: the "weight" operand differs per batch element (correlation GEMM: fmap2)
+  int B, h, w;
+  // epilogue
+  int epi, act, hidden;
+  float scale;
+  float div;  // EPI_F32: if non-zero, y = v / div instead of scale * v
+  __half* d0_hi;
+  __half* d0_lo;
+  int d0_stride, d0_choff;
+  __half* d1_hi;
+  __half* d1_lo;
+  int d1_stride, d1_choff;
+  float* f0;
+  float* f1;
+  float* f2;
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Store NV consecutive output channels [c, c+NV) of pixel `pix`; v holds acc (bias not yet added).
+// c is a multiple of NV; channel offsets of every destination are multiples of 8.
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int c, const float* v) {
+  if (c >= p.cout) return;
+  float y[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) y[i] = v[i] + ((p.bias && c + i < p.cout) ? __ldg(p.bias + c + i) : 0.f);
+  const bool full = (c + NV <= p.cout);
+
+  auto store_split = [&](__half* dhi, __half* dlo, int stride, int choff, int cc, const float* val) {
+    size_t off = (size_t)pix * stride + choff + cc;
+    if (full) {
+      __align__(16) __half h[NV];
+      __align__(16) __half l[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) split_f32(val[i], h[i], l[i]);
+      if constexpr (NV == 8) {
+        *reinterpret_cast<uint4*>(dhi + off) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(dlo + off) = *reinterpret_cast<const uint4*>(l);
+      } else if constexpr (NV == 4) {
+        *reinterpret_cast<uint2*>(dhi + off) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(dlo + off) = *reinterpret_cast<const uint2*>(l);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { dhi[off + i] = h[i]; dlo[off + i] = l[i]; }
+      }
+    } else {
+      for (int i = 0; i < NV; ++i)
+        if (c + i < p.cout) {
+          __half h, l;
+          split_f32(val[i], h, l);
+          dhi[off + i] = h;
+          dlo[off + i] = l;
+        }
+    }
+  };
+
+  switch (p.epi) {
+    case EPI_ACT: {
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      store_split(p.d0_hi, p.d0_lo, p.d0_stride, p.d0_choff, c, y);
+      if (p.d1_hi) store_split(p.d1_hi, p.d1_lo, p.d1_stride, p.d1_choff, c, y);
+    } break;
+    case EPI_ZR: {
+      // hidden is a multiple of NV (96, 128) so a group never straddles z|r
+      if (c < p.hidden) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) p.f0[(size_t)pix * p.hidden + c + i] = sigmoid_f(y[i]);
+      } else {
+        int ch = c - p.hidden;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) y[i] = sigmoid_f(y[i]) * p.f1[(size_t)pix * p.hidden + ch + i];
+        store_split(p.d0_hi, p.d0_lo, p.d0_stride, p.d0_choff, ch, y);
+      }
+    } break;
+    case EPI_Q: {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        size_t o = (size_t)pix * p.hidden + c + i;
+        float z = p.f0[o], hprev = p.f1[o];
+        float q = tanhf(y[i]);
+        float hn = (1.0f - z) * hprev + z * q;  // model_utils.py:147,155,168
+        p.f1[o] = hn;
+        y[i] = hn;
+      }
+      store_split(p.d0_hi, p.d0_lo, p.d0_stride, p.d0_choff, c, y);
+    } break;
+    case EPI_DELTA: {
+      for (int i = 0; i < NV; ++i)
+        if (c + i < 2) {
+          size_t o = (size_t)pix * 2 + c + i;
+          p.f1[o] = p.f1[o] + y[i];  // RAFT.py:102
+          if (p.f2) p.f2[o] = y[i];
+        }
+    } break;
+    case EPI_F32: {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (p.act == ACT_RELU) y[i] = fmaxf(y[i], 0.f);
+        y[i] = (p.div != 0.f) ? y[i] / p.div : p.scale * y[i];
+      }
+      float* dst = p.f0 + (size_t)pix * p.cout + c;
+      if (full && (p.cout & 3) == 0 && NV % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+      } else {
+        for (int i = 0; i < NV; ++i)
+          if (c + i < p.cout) dst[i] = y[i];
+      }
+    } break;
+  }
+}
+
+// back ends
+int launch_conv_simt(const ConvParams& p, cudaStream_t s);
+int launch_conv_tc(const ConvParams& p, cudaStream_t s);
+inline int launch_conv(const ConvParams& p, cudaStream_t s) {
+  return math_mode() == RB_MATH_SIMT ? launch_conv_simt(p, s) : launch_conv_tc(p, s);
+}
+
+inline int level_dim(int d, int level) { return d >> level; }
+
+}  // namespace rb

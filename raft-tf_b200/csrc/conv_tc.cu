@@ -1,0 +1,318 @@
+// tcgen05 implicit-GEMM convolution / GEMM over split fp16 operands (the RB_MATH_TC back end).
+//
+// One CTA computes a 128-pixel x BLOCK_N-channel output tile.  The 128 pixels are a BH x BW box of
+// one image, so for every filter tap the A operand is ONE TMA box load from the NHWC activation
+// at a shifted coordinate -- out-of-image pixels are zero-filled by TMA, which is exactly TF 'SAME'
+// zero padding for the stride-1 odd kernels of the update block.  Per (tap, 64-channel
+// chunk) a pipeline stage holds A_hi, A_lo (128x64 fp16 each) and [B_hi ; B_lo] (2*BLOCK_N x 64),
+// all 128-byte swizzled K-major.  Per 16-wide k-slice the MMA warp issues
+//     D[:, 0:2N]  (+)= A_hi x [B_hi ; B_lo]^T      (N' = 2*BLOCK_N)
+//     D[:, N:2N]   += A_lo x  B_hi^T
+// so TMEM columns [0,N) hold hi*hi and [N,2N) hold the two cross terms (2^11-scaled); the
+// epilogue forms hi*hi + 2^-11 * cross in fp32 and applies the fused epilogue of common.cuh.
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue (one TMEM lane
+// quarter each).
+#include <unordered_map>
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace rb {
+using namespace tc;
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled row
+constexpr int kATileBytes = kTileM * 128;  // 16 KB
+
+template <int BLOCK_N>
+struct TcCfg {
+  static constexpr int kBTileBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 4 ? 4 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileGeom {
+  int bw_log2, bh_log2;  // box = 2^bh x 2^bw pixels, product 128
+  int tiles_x, tiles_y;  // per image
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const ConvParams p, const TileGeom g) {
+  using Cfg = TcCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int b = blockIdx.x / tiles_per_img;
+  const int trem = blockIdx.x - b * tiles_per_img;
+  const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
+  const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int chunks = p.cin_pad / kChunkK;
+  const int taps = p.kh * p.kw;
+  const int kiters = taps * chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+      const int wb = p.w_per_batch ? b : 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        const int t = it / chunks, ck = it - t * chunks;
+        const int dy = t / p.kw - ph, dx = t % p.kw - pw;
+        const int c0 = p.in_choff + ck * kChunkK;
+        tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
+        tma_load_4d(&tmA_lo, &full_bar[s], st + kATileBytes, c0, x0 + dx, y0 + dy, b);
+        const int kcol = t * p.cin_pad + ck * kChunkK;
+        tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
+        tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
+      constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint64_t a_hi = umma_desc_sw128(st);
+        const uint64_t a_lo = umma_desc_sw128(st + kATileBytes);
+        const uint64_t b_all = umma_desc_sw128(st + 2 * kATileBytes);  // [B_hi ; B_lo], 2N rows
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) {
+          const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per k-slice, in 16-byte units
+          umma_f16(tmem_base, a_hi + koff, b_all + koff, idesc_2n, (it | k) != 0);
+          umma_f16(tmem_base + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) ----
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // tile row = pixel index inside the box
+    const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
+    const bool valid = (py < p.h) && (px < p.w);
+    const int pix = (b * p.h + py) * p.w + px;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      if (n0 + c >= p.cout) break;  // warp-uniform
+      uint32_t d0[16], d1[16];
+      tmem_ld16(trow + c, d0);
+      tmem_ld16(trow + BLOCK_N + c, d1);
+      tmem_ld_wait(d0, d1);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
+      if (valid) {
+        epilogue_store<8>(p, pix, n0 + c, v);
+        epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+namespace tc {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  RB_REQUIRE(fn, RB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RB_REQUIRE(r == CUDA_SUCCESS, RB_ERR_CUDA,
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+             rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return RB_OK;
+}
+}  // namespace tc
+
+// Tensor maps depend only on (pointer, geometry); cache them per thread so steady-state launches
+// (and CUDA-graph capture, which bakes kernel parameters) pay nothing for the encode.
+struct TmapKey {
+  const void* base;
+  uint64_t d[4];
+  uint64_t s[4];
+  uint32_t b[4];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h;
+  }
+};
+
+static int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.base = base;
+  for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.s[i] = (i + 1 < rank) ? strides[i] : 0; k.b[i] = box[i]; }
+  auto it = cache.find(k);
+  if (it != cache.end()) { *out = it->second; return RB_OK; }
+  int rc = make_tmap_f16(out, base, rank, dims, strides, box);
+  if (rc) return rc;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(k, *out);
+  return RB_OK;
+}
+
+static TileGeom choose_geom(int h, int w) {
+  TileGeom best{};
+  long best_tiles = -1;
+  for (int bwl = 7; bwl >= 3; --bwl) {
+    int bw = 1 << bwl, bh = kTileM >> bwl;
+    if (bw > w && bwl > 3) continue;  // keep the box inside the row when possible
+    long tiles = (long)((w + bw - 1) / bw) * ((h + bh - 1) / bh);
+    if (best_tiles < 0 || tiles < best_tiles) {
+      best_tiles = tiles;
+      best.bw_log2 = bwl; best.bh_log2 = 7 - bwl;
+      best.tiles_x = (w + bw - 1) / bw; best.tiles_y = (h + bh - 1) / bh;
+    }
+  }
+  return best;
+}
+
+// cycles per 16-wide k-slice: max(tensor math, shared-memory operand reads), see DESIGN.md
+static int slice_cycles(int n) {
+  int math = n + n / 2;
+  int smem = 64 + (3 * n) / 4;
+  return math > smem ? math : smem;
+}
+
+static int choose_block_n(int cout, long m_tiles) {
+  if (cout <= 16) return 16;
+  const int cand[4] = {128, 96, 64, 32};
+  int best = 128;
+  long best_cost = -1;
+  for (int i = 0; i < 4; ++i) {
+    int n = cand[i];
+    long tiles = m_tiles * ((cout + n - 1) / n);
+    long waves = (tiles + 147) / 148;
+    long cost = waves * slice_cycles(n);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = n; }
+  }
+  return best;
+}
+
+template <int BLOCK_N>
+static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap* maps, cudaStream_t s) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(p.B * g.tiles_x * g.tiles_y, (p.cout + BLOCK_N - 1) / BLOCK_N);
+  conv_tc_kernel<BLOCK_N><<<grid, 192, Cfg::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], p, g);
+  RB_CHECK_LAUNCH("conv_tc_kernel");
+  return RB_OK;
+}
+
+int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
+  RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
+             "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
+  const TileGeom g = choose_geom(p.h, p.w);
+  const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
+  const int bn = choose_block_n(p.cout, m_tiles);
+  CUtensorMap maps[4];
+  {
+    uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
+    uint64_t str[3] = {(uint64_t)p.in_stride * 2, (uint64_t)p.in_stride * 2 * p.w, (uint64_t)p.in_stride * 2 * p.w * p.h};
+    uint32_t box[4] = {(uint32_t)kChunkK, 1u << g.bw_log2, 1u << g.bh_log2, 1};
+    int rc;
+    if ((rc = cached_tmap(&maps[0], p.in_hi, 4, dims, str, box))) return rc;
+    if ((rc = cached_tmap(&maps[1], p.in_lo, 4, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t ktot = (uint64_t)p.kh * p.kw * p.cin_pad;
+    uint64_t dims[3] = {ktot, (uint64_t)p.cout_pad, (uint64_t)(p.w_per_batch ? p.B : 1)};
+    uint64_t str[2] = {ktot * 2, ktot * 2 * p.cout_pad};
+    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)bn, 1};
+    int rc;
+    if ((rc = cached_tmap(&maps[2], p.w_hi, 3, dims, str, box))) return rc;
+    if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
+  }
+  switch (bn) {
+    case 16: return launch_cfg<16>(p, g, maps, s);
+    case 32: return launch_cfg<32>(p, g, maps, s);
+    case 64: return launch_cfg<64>(p, g, maps, s);
+    case 96: return launch_cfg<96>(p, g, maps, s);
+    default: return launch_cfg<128>(p, g, maps, s);
+  }
+}
+
+}  // namespace rb

@@ -1,0 +1,506 @@
+// A5-A12: motion encoder, (Sep)ConvGRU, flow head, mask head and the iteration loop.
+// Reference: networks/model_utils.py:110-194, networks/RAFT.py:84-102.
+//
+// Data layout (per frame-pair batch, npix = B*h*w; every activation is a split fp16 tensor
+// [npix][C] = hi plane followed by lo plane, see common.cuh):
+//   CORR [Ccorr]  lookup output, 4*(2r+1)^2 channels zero-padded to a multiple of 64
+//   C1   [256]    relu(convc1)                                   (things only)
+//   CF   [cf]     [cor | flo]      = input of encoder/conv       (model_utils.py:117,127)
+//   F1   [f1]     relu(convf1)
+//   HX   [hx]     [h | inp | motion_out | flow | 0-pad] = GRU z/r input (cat_hx, :141,150,160)
+//   QX   [hx]     [r*h | inp | motion_out | flow | 0-pad] = GRU q input (:144,153,165)
+//   FH   [fh]     relu(flow_head/conv1); reused for relu(mask/0)
+//   H, Z fp32 [hidden]  recurrent state and the update gate
+// Concatenations are never materialised: producers write at channel offsets of HX/QX/CF.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace rb {
+
+int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
+                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// static description of the two variants
+// ---------------------------------------------------------------------------------------------
+struct RefConv {
+  const char* name;
+  int kh, kw, cin, cout;
+};
+
+static const RefConv kThingsConvs[] = {
+    {"update_block/encoder/convc1", 1, 1, 324, 256}, {"update_block/encoder/convc2", 3, 3, 256, 192},
+    {"update_block/encoder/convf1", 7, 7, 2, 128},   {"update_block/encoder/convf2", 3, 3, 128, 64},
+    {"update_block/encoder/conv", 3, 3, 256, 126},   {"update_block/gru/convz1", 1, 5, 384, 128},
+    {"update_block/gru/convr1", 1, 5, 384, 128},     {"update_block/gru/convq1", 1, 5, 384, 128},
+    {"update_block/gru/convz2", 5, 1, 384, 128},     {"update_block/gru/convr2", 5, 1, 384, 128},
+    {"update_block/gru/convq2", 5, 1, 384, 128},     {"update_block/flow_head/conv1", 3, 3, 128, 256},
+    {"update_block/flow_head/conv2", 3, 3, 256, 2},  {"update_block/mask/0", 3, 3, 128, 256},
+    {"update_block/mask/2", 1, 1, 256, 576}};
+static const RefConv kSmallConvs[] = {
+    {"update_block/encoder/convc1", 1, 1, 196, 96}, {"update_block/encoder/convf1", 7, 7, 2, 64},
+    {"update_block/encoder/convf2", 3, 3, 64, 32},  {"update_block/encoder/conv", 3, 3, 128, 80},
+    {"update_block/gru/convz", 3, 3, 242, 96},      {"update_block/gru/convr", 3, 3, 242, 96},
+    {"update_block/gru/convq", 3, 3, 242, 96},      {"update_block/flow_head/conv1", 3, 3, 96, 128},
+    {"update_block/flow_head/conv2", 3, 3, 128, 2}};
+
+// packed (device) convs; src = indices into the reference list (two for the merged z|r conv)
+enum PackedId {
+  P_CONVC1 = 0, P_CONVC2, P_CONVF2, P_MOTION, P_ZR1, P_Q1, P_ZR2, P_Q2, P_FH1, P_FH2, P_MASK0, P_MASK2, P_COUNT
+};
+struct PackedConv {
+  int src0, src1;  // reference conv indices (-1 = none)
+  int cin_pad;
+};
+
+struct Variant {
+  int small, hidden, ctx, radius, corr_ch, corr_pad, c1, cf, cor, f1, hx, fh, mo_out, nref;
+  const RefConv* ref;
+  int convf1_ref;
+  PackedConv pk[P_COUNT];
+};
+
+static const Variant kThings = {
+    0, 128, 128, 4, 324, 384, 256, 256, 192, 128, 384, 256, 126, 15, kThingsConvs, 2,
+    {{0, -1, 384}, {1, -1, 256}, {3, -1, 128}, {4, -1, 256}, {5, 6, 384}, {7, -1, 384}, {8, 9, 384},
+     {10, -1, 384}, {11, -1, 128}, {12, -1, 256}, {13, -1, 128}, {14, -1, 256}}};
+static const Variant kSmall = {
+    1, 96, 64, 3, 196, 256, 0, 128, 96, 64, 256, 128, 80, 9, kSmallConvs, 1,
+    {{0, -1, 256}, {-1, -1, 0}, {2, -1, 64}, {3, -1, 128}, {4, 5, 256}, {6, -1, 256}, {-1, -1, 0},
+     {-1, -1, 0}, {7, -1, 128}, {8, -1, 128}, {-1, -1, 0}, {-1, -1, 0}}};
+
+static inline const Variant& variant(int small) { return small ? kSmall : kThings; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+// ---- packed weight blob -------------------------------------------------------------------------
+struct PackedLayout {
+  size_t hi[P_COUNT], lo[P_COUNT], bias[P_COUNT];  // byte offsets
+  int cout[P_COUNT], cout_pad[P_COUNT], kh[P_COUNT], kw[P_COUNT];
+  size_t f1_w, f1_b;  // convf1: fp32 [49*2][cout] and bias
+  size_t total;
+};
+
+static PackedLayout packed_layout(const Variant& v) {
+  PackedLayout L;
+  memset(&L, 0, sizeof(L));
+  size_t off = 0;
+  for (int i = 0; i < P_COUNT; ++i) {
+    const PackedConv& pc = v.pk[i];
+    if (pc.src0 < 0) continue;
+    const RefConv& r0 = v.ref[pc.src0];
+    int cout = r0.cout + (pc.src1 >= 0 ? v.ref[pc.src1].cout : 0);
+    L.cout[i] = cout;
+    L.cout_pad[i] = pad16(cout);
+    L.kh[i] = r0.kh;
+    L.kw[i] = r0.kw;
+    size_t plane = (size_t)L.cout_pad[i] * r0.kh * r0.kw * pc.cin_pad * sizeof(__half);
+    L.hi[i] = off; off = align_up(off + plane, 256);
+    L.lo[i] = off; off = align_up(off + plane, 256);
+    L.bias[i] = off; off = align_up(off + (size_t)L.cout_pad[i] * sizeof(float), 256);
+  }
+  const RefConv& f = v.ref[v.convf1_ref];
+  L.f1_w = off; off = align_up(off + (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float), 256);
+  L.f1_b = off; off = align_up(off + (size_t)f.cout * sizeof(float), 256);
+  L.total = off;
+  return L;
+}
+
+// ---- activation workspace -------------------------------------------------------------------------
+struct Workspace {
+  SplitPtr corr, c1, cf, f1, hx, qx, fh;
+  float* H;
+  float* Z;
+  size_t total;
+};
+
+static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
+  Workspace W;
+  char* b = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto split = [&](int C) {
+    SplitPtr sp;
+    size_t plane = align_up(npix * (size_t)C * sizeof(__half), 1024);
+    sp.hi = reinterpret_cast<__half*>(b + off);
+    sp.lo = reinterpret_cast<__half*>(b + off + plane);
+    off += 2 * plane;
+    return sp;
+  };
+  W.corr = split(v.corr_pad);
+  W.c1 = split(v.c1 > 0 ? v.c1 : 64);
+  W.cf = split(v.cf);
+  W.f1 = split(v.f1);
+  W.hx = split(v.hx);
+  W.qx = split(v.hx);
+  W.fh = split(v.fh);
+  size_t fsz = align_up(npix * (size_t)v.hidden * sizeof(float), 1024);
+  W.H = reinterpret_cast<float*>(b + off); off += fsz;
+  W.Z = reinterpret_cast<float*>(b + off); off += fsz;
+  W.total = off;
+  return W;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void set_state_kernel(const float* __restrict__ net, const float* __restrict__ inp, Workspace W,
+                                 int npix, int hidden, int ctx, int hx) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int per = hidden + ctx;
+  if (i >= (size_t)npix * per) return;
+  int pix = i / per, c = i % per;
+  __half hi, lo;
+  if (c < hidden) {
+    float v = net[(size_t)pix * hidden + c];
+    W.H[(size_t)pix * hidden + c] = v;
+    split_f32(v, hi, lo);
+    W.hx.hi[(size_t)pix * hx + c] = hi;
+    W.hx.lo[(size_t)pix * hx + c] = lo;
+  } else {
+    float v = inp[(size_t)pix * ctx + (c - hidden)];
+    split_f32(v, hi, lo);
+    size_t o = (size_t)pix * hx + c;
+    W.hx.hi[o] = hi; W.hx.lo[o] = lo;
+    W.qx.hi[o] = hi; W.qx.lo[o] = lo;
+  }
+}
+
+__global__ void set_corr_kernel(const float* __restrict__ corr, SplitPtr dst, int npix, int ch, int stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)npix * ch) return;
+  int pix = i / ch, c = i % ch;
+  __half hi, lo;
+  split_f32(corr[i], hi, lo);
+  dst.hi[(size_t)pix * stride + c] = hi;
+  dst.lo[(size_t)pix * stride + c] = lo;
+}
+
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// encoder/convf1: 7x7 conv over the 2-channel flow + ReLU (model_utils.py:114,124), CUDA cores
+// (K = 98 is no tensor-core shape).  flow = coords1 - coords_grid (RAFT.py:95) is formed while
+// staging; SAME padding zero-pads the FLOW.  One thread per output channel, 32-pixel row segment
+// per block; the flow itself is also written into the [.., flow] slot of HX/QX (concat_out, :119).
+template <int COUT>
+__global__ void __launch_bounds__(COUT) flow_conv7_kernel(const float2* __restrict__ coords1,
+                                                          const float* __restrict__ Wf,  // [98][COUT]
+                                                          const float* __restrict__ bf, SplitPtr f1,
+                                                          int f1_stride, SplitPtr hx, SplitPtr qx,
+                                                          int hx_stride, int flow_choff, int h, int w) {
+  constexpr int SEG = 32;
+  __shared__ float2 patch[7][SEG + 6];
+  const int x0 = blockIdx.x * SEG, y = blockIdx.y, b = blockIdx.z;
+  const int c = threadIdx.x;
+  for (int e = threadIdx.x; e < 7 * (SEG + 6); e += COUT) {
+    int py = e / (SEG + 6), px = e % (SEG + 6);
+    int sy = y + py - 3, sx = x0 + px - 3;
+    float2 f = make_float2(0.f, 0.f);
+    if (sy >= 0 && sy < h && sx >= 0 && sx < w) {
+      float2 cc = coords1[(size_t)(b * h + sy) * w + sx];
+      f = make_float2(cc.x - (float)sx, cc.y - (float)sy);
+    }
+    patch[py][px] = f;
+  }
+  float wr[98];
+#pragma unroll
+  for (int k = 0; k < 98; ++k) wr[k] = Wf[k * COUT + c];
+  const float bias = bf[c];
+  __syncthreads();
+  for (int px = 0; px < SEG; ++px) {
+    int x = x0 + px;
+    if (x >= w) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        float2 f = patch[ky][px + kx];
+        acc = fmaf(wr[(ky * 7 + kx) * 2 + 0], f.x, acc);
+        acc = fmaf(wr[(ky * 7 + kx) * 2 + 1], f.y, acc);
+      }
+    acc = fmaxf(acc + bias, 0.f);
+    size_t pix = (size_t)(b * h + y) * w + x;
+    __half hi, lo;
+    split_f32(acc, hi, lo);
+    f1.hi[pix * f1_stride + c] = hi;
+    f1.lo[pix * f1_stride + c] = lo;
+    if (c < 2) {
+      float2 f = patch[3][px + 3];
+      split_f32(c == 0 ? f.x : f.y, hi, lo);
+      size_t o = pix * hx_stride + flow_choff + c;
+      hx.hi[o] = hi; hx.lo[o] = lo;
+      qx.hi[o] = hi; qx.lo[o] = lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one update-block application
+// ---------------------------------------------------------------------------------------------
+static ConvParams base_params(const Variant& v, const PackedLayout& L, const void* blob, int id, SplitPtr in,
+                              int in_stride, int in_choff, int B, int h, int w) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  const char* bb = reinterpret_cast<const char*>(blob);
+  p.in_hi = in.hi; p.in_lo = in.lo; p.in_stride = in_stride; p.in_choff = in_choff;
+  p.cin_pad = v.pk[id].cin_pad;
+  p.w_hi = reinterpret_cast<const __half*>(bb + L.hi[id]);
+  p.w_lo = reinterpret_cast<const __half*>(bb + L.lo[id]);
+  p.bias = reinterpret_cast<const float*>(bb + L.bias[id]);
+  p.cout = L.cout[id]; p.cout_pad = L.cout_pad[id]; p.kh = L.kh[id]; p.kw = L.kw[id];
+  p.B = B; p.h = h; p.w = w;
+  p.hidden = v.hidden; p.scale = 1.f;
+  return p;
+}
+
+static void set_act(ConvParams& p, int act, SplitPtr d0, int stride0, int choff0) {
+  p.epi = EPI_ACT; p.act = act;
+  p.d0_hi = d0.hi; p.d0_lo = d0.lo; p.d0_stride = stride0; p.d0_choff = choff0;
+}
+
+static int update_step(const Variant& v, const void* blob, void* wsp, float* coords1, float* delta_out,
+                       float* mask_out, int B, int h, int w, cudaStream_t s) {
+  const size_t npix = (size_t)B * h * w;
+  const PackedLayout L = packed_layout(v);
+  const Workspace W = workspace_layout(v, npix, wsp);
+  const char* bb = reinterpret_cast<const char*>(blob);
+  const int xoff = v.hidden + v.ctx;      // channel offset of motion_out inside HX/QX
+  const int foff = xoff + v.mo_out;       // channel offset of the raw flow
+  int rc;
+  // ---- motion encoder (model_utils.py:110-129) ----
+  {
+    dim3 grid((w + 31) / 32, h, B);
+    const float* Wf = reinterpret_cast<const float*>(bb + L.f1_w);
+    const float* bf = reinterpret_cast<const float*>(bb + L.f1_b);
+    const float2* c1 = reinterpret_cast<const float2*>(coords1);
+    if (v.small) flow_conv7_kernel<64><<<grid, 64, 0, s>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
+    else flow_conv7_kernel<128><<<grid, 128, 0, s>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
+    RB_CHECK_LAUNCH("flow_conv7_kernel");
+  }
+  if (!v.small) {
+    ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
+    set_act(p, ACT_RELU, W.c1, v.c1, 0);
+    if ((rc = launch_conv(p, s))) return rc;
+    p = base_params(v, L, blob, P_CONVC2, W.c1, v.c1, 0, B, h, w);
+    set_act(p, ACT_RELU, W.cf, v.cf, 0);
+    if ((rc = launch_conv(p, s))) return rc;
+  } else {
+    ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
+    set_act(p, ACT_RELU, W.cf, v.cf, 0);
+    if ((rc = launch_conv(p, s))) return rc;
+  }
+  {
+    ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
+    set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
+    if ((rc = launch_conv(p, s))) return rc;
+    p = base_params(v, L, blob, P_MOTION, W.cf, v.cf, 0, B, h, w);
+    set_act(p, ACT_RELU, W.hx, v.hx, xoff);
+    p.d1_hi = W.qx.hi; p.d1_lo = W.qx.lo; p.d1_stride = v.hx; p.d1_choff = xoff;
+    if ((rc = launch_conv(p, s))) return rc;
+  }
+  // ---- GRU (model_utils.py:138-169) ----
+  const int passes = v.small ? 1 : 2;
+  for (int pass = 0; pass < passes; ++pass) {
+    int zr = pass == 0 ? P_ZR1 : P_ZR2, q = pass == 0 ? P_Q1 : P_Q2;
+    ConvParams p = base_params(v, L, blob, zr, W.hx, v.hx, 0, B, h, w);
+    p.epi = EPI_ZR; p.f0 = W.Z; p.f1 = W.H;
+    p.d0_hi = W.qx.hi; p.d0_lo = W.qx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
+    if ((rc = launch_conv(p, s))) return rc;
+    p = base_params(v, L, blob, q, W.qx, v.hx, 0, B, h, w);
+    p.epi = EPI_Q; p.f0 = W.Z; p.f1 = W.H;
+    p.d0_hi = W.hx.hi; p.d0_lo = W.hx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
+    if ((rc = launch_conv(p, s))) return rc;
+  }
+  // ---- flow head (model_utils.py:131-135) + coords1 += delta (RAFT.py:102) ----
+  {
+    ConvParams p = base_params(v, L, blob, P_FH1, W.hx, v.hx, 0, B, h, w);
+    set_act(p, ACT_RELU, W.fh, v.fh, 0);
+    if ((rc = launch_conv(p, s))) return rc;
+    p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
+    p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
+    if ((rc = launch_conv(p, s))) return rc;
+  }
+  // ---- mask head (model_utils.py:180-183); only the last iteration's mask is ever consumed ----
+  if (mask_out) {
+    RB_REQUIRE(!v.small, RB_ERR_UNSUPPORTED, "raft-small has no mask head (model_utils.py:194)");
+    ConvParams p = base_params(v, L, blob, P_MASK0, W.hx, v.hx, 0, B, h, w);
+    set_act(p, ACT_RELU, W.fh, v.fh, 0);
+    if ((rc = launch_conv(p, s))) return rc;
+    p = base_params(v, L, blob, P_MASK2, W.fh, v.fh, 0, B, h, w);
+    p.epi = EPI_F32; p.f0 = mask_out; p.scale = 0.25f;
+    if ((rc = launch_conv(p, s))) return rc;
+  }
+  return RB_OK;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+static int check_shape(const char* fn, int B, int h, int w) {
+  RB_REQUIRE(B > 0 && h > 0 && w > 0 && (size_t)B * h * w < (1u << 30), RB_ERR_BAD_SHAPE, "%s: bad shape B=%d h=%d w=%d",
+             fn, B, h, w);
+  return RB_OK;
+}
+
+extern "C" int rb_update_num_convs(int small) { return variant(small).nref; }
+
+extern "C" const char* rb_update_conv_name(int small, int i) {
+  const Variant& v = variant(small);
+  if (i < 0 || i >= v.nref) return nullptr;
+  return v.ref[i].name;
+}
+
+extern "C" int rb_update_conv_shape(int small, int i, int* kh, int* kw, int* cin, int* cout) {
+  const Variant& v = variant(small);
+  RB_REQUIRE(i >= 0 && i < v.nref, RB_ERR_BAD_ARG, "rb_update_conv_shape: index %d out of range", i);
+  if (kh) *kh = v.ref[i].kh;
+  if (kw) *kw = v.ref[i].kw;
+  if (cin) *cin = v.ref[i].cin;
+  if (cout) *cout = v.ref[i].cout;
+  return RB_OK;
+}
+
+extern "C" int rb_update_weights_bytes(int small, size_t* bytes) {
+  RB_REQUIRE(bytes, RB_ERR_BAD_ARG, "rb_update_weights_bytes: null output");
+  *bytes = packed_layout(variant(small)).total;
+  return RB_OK;
+}
+
+extern "C" int rb_update_weights_pack(int small, const float* const* W_host, const float* const* b_host,
+                                      void* blob, size_t blob_bytes, void* stream) {
+  const Variant& v = variant(small);
+  const PackedLayout L = packed_layout(v);
+  RB_REQUIRE(W_host && b_host && blob, RB_ERR_BAD_ARG, "rb_update_weights_pack: null pointer");
+  RB_REQUIRE(blob_bytes >= L.total, RB_ERR_WORKSPACE, "rb_update_weights_pack: blob has %zu bytes, need %zu",
+             blob_bytes, L.total);
+  for (int i = 0; i < v.nref; ++i)
+    RB_REQUIRE(W_host[i] && b_host[i], RB_ERR_BAD_ARG, "rb_update_weights_pack: missing weights for %s", v.ref[i].name);
+  std::vector<char> host(L.total, 0);
+  for (int id = 0; id < P_COUNT; ++id) {
+    const PackedConv& pc = v.pk[id];
+    if (pc.src0 < 0) continue;
+    __half* hi = reinterpret_cast<__half*>(host.data() + L.hi[id]);
+    __half* lo = reinterpret_cast<__half*>(host.data() + L.lo[id]);
+    float* bias = reinterpret_cast<float*>(host.data() + L.bias[id]);
+    const int taps = L.kh[id] * L.kw[id];
+    int co_base = 0;
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      int src = sidx == 0 ? pc.src0 : pc.src1;
+      if (src < 0) continue;
+      const RefConv& r = v.ref[src];
+      RB_REQUIRE(r.cin <= pc.cin_pad, RB_ERR_BAD_SHAPE, "internal: cin_pad too small for %s", r.name);
+      const float* Wsrc = W_host[src];  // HWIO
+      for (int t = 0; t < taps; ++t)
+        for (int ci = 0; ci < r.cin; ++ci)
+          for (int co = 0; co < r.cout; ++co) {
+            float val = Wsrc[((size_t)t * r.cin + ci) * r.cout + co];
+            size_t o = ((size_t)(co_base + co) * taps + t) * pc.cin_pad + ci;
+            split_f32(val, hi[o], lo[o]);
+          }
+      for (int co = 0; co < r.cout; ++co) bias[co_base + co] = b_host[src][co];
+      co_base += r.cout;
+    }
+  }
+  {
+    const RefConv& f = v.ref[v.convf1_ref];
+    memcpy(host.data() + L.f1_w, W_host[v.convf1_ref], (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float));
+    memcpy(host.data() + L.f1_b, b_host[v.convf1_ref], (size_t)f.cout * sizeof(float));
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), L.total, cudaMemcpyHostToDevice, s));
+  RB_CHECK_CUDA(cudaStreamSynchronize(s));  // `host` dies at return; packing is an init-time call
+  return RB_OK;
+}
+
+extern "C" int rb_update_workspace_bytes(int small, int B, int h, int w, size_t* bytes) {
+  RB_REQUIRE(bytes, RB_ERR_BAD_ARG, "rb_update_workspace_bytes: null output");
+  int rc = check_shape("rb_update_workspace_bytes", B, h, w);
+  if (rc) return rc;
+  *bytes = workspace_layout(variant(small), (size_t)B * h * w, nullptr).total;
+  return RB_OK;
+}
+
+extern "C" int rb_update_set_state(int small, void* workspace, const float* net, const float* inp, int B, int h,
+                                   int w, void* stream) {
+  RB_REQUIRE(workspace && net && inp, RB_ERR_BAD_ARG, "rb_update_set_state: null pointer");
+  int rc = check_shape("rb_update_set_state", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  size_t npix = (size_t)B * h * w;
+  Workspace W = workspace_layout(v, npix, workspace);
+  size_t n = npix * (v.hidden + v.ctx);
+  set_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(net, inp, W, (int)npix, v.hidden,
+                                                                                  v.ctx, v.hx);
+  RB_CHECK_LAUNCH("set_state_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_update_get_net(int small, const void* workspace, float* net, int B, int h, int w, void* stream) {
+  RB_REQUIRE(workspace && net, RB_ERR_BAD_ARG, "rb_update_get_net: null pointer");
+  int rc = check_shape("rb_update_get_net", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  size_t npix = (size_t)B * h * w;
+  Workspace W = workspace_layout(v, npix, const_cast<void*>(workspace));
+  size_t n = npix * v.hidden;
+  copy_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W.H, net, n);
+  RB_CHECK_LAUNCH("copy_f32_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_update_lookup(int small, void* workspace, const float* pyramid, const float* coords1, int B,
+                                int h, int w, void* stream) {
+  RB_REQUIRE(workspace && pyramid && coords1, RB_ERR_BAD_ARG, "rb_update_lookup: null pointer");
+  int rc = check_shape("rb_update_lookup", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  Workspace W = workspace_layout(v, (size_t)B * h * w, workspace);
+  return launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int rb_update_set_corr(int small, void* workspace, const float* corr, int B, int h, int w,
+                                  void* stream) {
+  RB_REQUIRE(workspace && corr, RB_ERR_BAD_ARG, "rb_update_set_corr: null pointer");
+  int rc = check_shape("rb_update_set_corr", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  size_t npix = (size_t)B * h * w;
+  Workspace W = workspace_layout(v, npix, workspace);
+  size_t n = npix * v.corr_ch;
+  set_corr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(corr, W.corr, (int)npix, v.corr_ch,
+                                                                                 v.corr_pad);
+  RB_CHECK_LAUNCH("set_corr_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_update_step(int small, const void* weights, void* workspace, float* coords1, float* delta_out,
+                              float* mask_out, int B, int h, int w, void* stream) {
+  RB_REQUIRE(weights && workspace && coords1, RB_ERR_BAD_ARG, "rb_update_step: null pointer");
+  int rc = check_shape("rb_update_step", B, h, w);
+  if (rc) return rc;
+  return update_step(variant(small), weights, workspace, coords1, delta_out, mask_out, B, h, w, (cudaStream_t)stream);
+}
+
+extern "C" int rb_raft_iterate(int small, const void* weights, void* workspace, const float* pyramid,
+                               float* coords1, float* mask_out, int B, int h, int w, int iters, void* stream) {
+  RB_REQUIRE(weights && workspace && pyramid && coords1, RB_ERR_BAD_ARG, "rb_raft_iterate: null pointer");
+  RB_REQUIRE(iters >= 1, RB_ERR_BAD_ARG, "rb_raft_iterate: iters=%d", iters);
+  RB_REQUIRE(small || mask_out, RB_ERR_BAD_ARG, "rb_raft_iterate: raft-things needs mask_out");
+  int rc = check_shape("rb_raft_iterate", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  for (int it = 0; it < iters; ++it) {
+    if ((rc = rb_update_lookup(small, workspace, pyramid, coords1, B, h, w, stream))) return rc;
+    float* m = (it == iters - 1 && !small) ? mask_out : nullptr;
+    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream))) return rc;
+  }
+  return RB_OK;
+}
