@@ -32,8 +32,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFF) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+        printf("raft_b200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, parity);
+        __trap();
+      }
+    }
   }
 }
 

@@ -4,7 +4,7 @@ import os
 import sys
 import traceback
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "raft-tf_b200"))
 import numpy as np
