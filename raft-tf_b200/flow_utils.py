@@ -1,0 +1,45 @@
+"""Flow colour coding used by the CLI (the reference's infer_raft.py:25,43 calls
+flow_utils.flow_to_color(flow, convert_to_bgr=True)).  Independent numpy implementation of the
+Middlebury colour wheel (Baker et al., ICCV 2007): same normalisation by the maximum radius
+(+1e-5) and floor(255*col) quantisation as the reference's flow_utils.py:95-121."""
+import numpy as np
+
+_SEGMENTS = (("RY", 15), ("YG", 6), ("GC", 4), ("CB", 11), ("BM", 13), ("MR", 6))
+
+
+def make_colorwheel():
+    n = sum(k for _, k in _SEGMENTS)
+    wheel = np.zeros((n, 3))
+    # each segment ramps one channel up or down while another stays saturated
+    plan = [(0, 1, +1), (1, 0, -1), (1, 2, +1), (2, 1, -1), (2, 0, +1), (0, 2, -1)]
+    pos = 0
+    for (_, k), (sat, ramp, sign) in zip(_SEGMENTS, plan):
+        t = np.floor(255 * np.arange(k) / k)
+        wheel[pos:pos + k, sat] = 255
+        wheel[pos:pos + k, ramp] = t if sign > 0 else 255 - t
+        pos += k
+    return wheel
+
+
+def flow_to_color(flow_uv, clip_flow=None, convert_to_bgr=False):
+    assert flow_uv.ndim == 3 and flow_uv.shape[2] == 2
+    if clip_flow is not None:
+        flow_uv = np.clip(flow_uv, 0, clip_flow)
+    u, v = flow_uv[..., 0].astype(np.float64), flow_uv[..., 1].astype(np.float64)
+    rmax = np.sqrt(u * u + v * v).max()
+    u, v = u / (rmax + 1e-5), v / (rmax + 1e-5)
+    wheel = make_colorwheel()
+    n = wheel.shape[0]
+    rad = np.sqrt(u * u + v * v)
+    fk = (np.arctan2(-v, -u) / np.pi + 1) / 2 * (n - 1) + 1
+    k0 = np.minimum(np.floor(fk).astype(np.int32), n - 2)
+    k1 = k0 + 1
+    k1[k1 == n] = 1
+    f = fk - k0
+    img = np.zeros(u.shape + (3,), np.uint8)
+    for ch in range(3):
+        col = (1 - f) * wheel[k0, ch] / 255.0 + f * wheel[k1, ch] / 255.0
+        inside = rad <= 1
+        col = np.where(inside, 1 - rad * (1 - col), col * 0.75)
+        img[..., 2 - ch if convert_to_bgr else ch] = np.floor(255 * col)
+    return img
