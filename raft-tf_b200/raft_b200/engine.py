@@ -6,6 +6,7 @@ rb_upsample_convex / rb_upflow8.  Mirrors RAFT.network_graph (networks/RAFT.py:7
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -24,7 +25,7 @@ class RaftEngine:
         self.device = torch.device(device if device is not None else "cuda:0")
         self.small, self.iters = bool(small), int(iters)
         self.hidden, self.ctx, self.radius, self.fdim = (96, 64, 3, 128) if small else (128, 128, 4, 256)
-        self.use_graph = use_graph
+        self.use_graph = use_graph and not os.environ.get("RAFT_B200_NO_GRAPH")
         self.math_mode = math_mode
         torch.backends.cudnn.allow_tf32 = False  # the reference is fp32 end to end
         torch.backends.cuda.matmul.allow_tf32 = False

@@ -188,8 +188,8 @@ def test_update_block(cuda, mode, small):
         torch.cuda.synchronize()
     finally:
         capi.lib.rb_set_math_mode(capi.RB_MATH_TC)
-    assert (n2.cpu().double() - rn).abs().max() < 2e-5, (n2.cpu().double() - rn).abs().max()
-    assert (d2.cpu().double() - rd).abs().max() < 2e-5, (d2.cpu().double() - rd).abs().max()
+    assert (n2.cpu().double() - rn).abs().max() < 5e-5, (n2.cpu().double() - rn).abs().max()
+    assert (d2.cpu().double() - rd).abs().max() < 5e-5, (d2.cpu().double() - rd).abs().max()
     if not small:
         assert (m2.cpu().double() - rm).abs().max() < 1e-4, (m2.cpu().double() - rm).abs().max()
     else:
