@@ -248,21 +248,37 @@ def main():
     npix = B * h * w
     lib = capi.lib
 
-    def ev_time(fn, reps=20):
-        ts = []
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) / 1e3)
-        return statistics.median(ts)
+    def ev_time(fn, reps=10, flush_l2=True):
+        """Device time of fn() per call: `reps` x (L2 flush; fn) replayed from one CUDA graph minus the same graph
+        without fn -- event timing of eager launches would measure the host launch latency for ~5 us kernels."""
+        def build(with_fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    if flush_l2:
+                        flush.zero_()
+                    if with_fn:
+                        fn()
+            return g
+        fn(); torch.cuda.synchronize()
+        g1, g0 = build(True), build(False)
+        def run(g):
+            ts = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); g.replay(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) / 1e3)
+            return statistics.median(ts)
+        return max(run(g1) - run(g0), 1e-9) / reps
 
     c1 = eng.coords1.clone()
     t_upd = ev_time(lambda: capi.check(lib.rb_update_step(s, capi.ptr(eng.blob), capi.ptr(eng.ws), capi.ptr(c1), None, None,
                                                            B, h, w, capi.stream())))
-    t_look = ev_time(lambda: capi.check(lib.rb_update_lookup(s, capi.ptr(eng.ws), capi.ptr(eng.pyramid), capi.ptr(eng.coords1),
-                                                             B, h, w, capi.stream())))
+    look = lambda: capi.check(lib.rb_update_lookup(s, capi.ptr(eng.ws), capi.ptr(eng.pyramid), capi.ptr(eng.coords1),  # noqa: E731
+                                                   B, h, w, capi.stream()))
+    t_look = ev_time(look)
+    t_look_warm = ev_time(look, flush_l2=False)
     upd_flops = 2.0 * npix * UPDATE_MAC_PER_PX
     look_bytes = float(npix * LOOKUP_BYTES_PER_PX)
     roof = {"kernel": "rb_update_step (11 conv_tc_kernel launches + flow_conv7)", "bound": "tensor",
@@ -272,7 +288,9 @@ def main():
             "us_per_launch_group": t_upd * 1e6}
     roof_l = {"kernel": "corr_lookup_kernel<4,split>", "bound": "hbm", "achieved": look_bytes / t_look / 1e9,
               "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": None,
-              "peak_source": pk["src"], "us_per_launch": t_look * 1e6}
+              "peak_source": pk["src"], "us_per_launch": t_look * 1e6,
+              "l2_warm": {"us_per_launch": t_look_warm * 1e6, "achieved": look_bytes / t_look_warm / 1e9,
+                          "note": "same launch without the L2 flush: at B=1 the ~25 MB of patches around the current flow stay L2-resident between iterations"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

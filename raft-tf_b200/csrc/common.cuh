@@ -114,6 +114,27 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
   for (int i = 0; i < NV; ++i) y[i] = v[i] + ((p.bias && c + i < p.cout) ? __ldg(p.bias + c + i) : 0.f);
   const bool full = (c + NV <= p.cout);
 
+  auto load_f32 = [&](const float* src, float* dst) {  // NV consecutive floats, 4*NV-byte aligned
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + i);
+        dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) dst[i] = src[i];
+    }
+  };
+  auto store_f32 = [&](float* dst, const float* src) {
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) dst[i] = src[i];
+    }
+  };
   auto store_split = [&](__half* dhi, __half* dlo, int stride, int choff, int cc, const float* val) {
     size_t off = (size_t)pix * stride + choff + cc;
     if (full) {
@@ -152,27 +173,33 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
       if (p.d1_hi) store_split(p.d1_hi, p.d1_lo, p.d1_stride, p.d1_choff, c, y);
     } break;
     case EPI_ZR: {
-      // hidden is a multiple of NV (96, 128) so a group never straddles z|r
+      // hidden is a multiple of NV (96, 128) so a group never straddles z|r.  All loads are issued
+      // before any store: f0/f1 may alias as far as the compiler knows, and interleaving them would
+      // serialise one L2 round trip per channel.
       if (c < p.hidden) {
+        float z[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) p.f0[(size_t)pix * p.hidden + c + i] = sigmoid_f(y[i]);
+        for (int i = 0; i < NV; ++i) z[i] = sigmoid_f(y[i]);
+        store_f32(p.f0 + (size_t)pix * p.hidden + c, z);
       } else {
-        int ch = c - p.hidden;
+        const int ch = c - p.hidden;
+        float hprev[NV];
+        load_f32(p.f1 + (size_t)pix * p.hidden + ch, hprev);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) y[i] = sigmoid_f(y[i]) * p.f1[(size_t)pix * p.hidden + ch + i];
+        for (int i = 0; i < NV; ++i) y[i] = sigmoid_f(y[i]) * hprev[i];
         store_split(p.d0_hi, p.d0_lo, p.d0_stride, p.d0_choff, ch, y);
       }
     } break;
     case EPI_Q: {
+      float z[NV], hprev[NV];
+      load_f32(p.f0 + (size_t)pix * p.hidden + c, z);
+      load_f32(p.f1 + (size_t)pix * p.hidden + c, hprev);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        size_t o = (size_t)pix * p.hidden + c + i;
-        float z = p.f0[o], hprev = p.f1[o];
-        float q = tanhf(y[i]);
-        float hn = (1.0f - z) * hprev + z * q;  // model_utils.py:147,155,168
-        p.f1[o] = hn;
-        y[i] = hn;
+        const float q = tanhf(y[i]);
+        y[i] = (1.0f - z[i]) * hprev[i] + z[i] * q;  // model_utils.py:147,155,168
       }
+      store_f32(p.f1 + (size_t)pix * p.hidden + c, y);
       store_split(p.d0_hi, p.d0_lo, p.d0_stride, p.d0_choff, c, y);
     } break;
     case EPI_DELTA: {

@@ -10,8 +10,9 @@
 //     D[:, N:2N]   += A_lo x  B_hi^T
 // so TMEM columns [0,N) hold hi*hi and [N,2N) hold the two cross terms (2^11-scaled); the
 // epilogue forms hi*hi + 2^-11 * cross in fp32 and applies the fused epilogue of common.cuh.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue (one TMEM lane
-// quarter each).
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue: warp w reads TMEM lane
+// quarter (w % 4) and, when BLOCK_N >= 32, column half (w - 2) / 4 (profiles/r01: the epilogue, not
+// the MMA loop, was the longer phase with 4 warps).
 #include <unordered_map>
 #include <string.h>
 
@@ -23,6 +24,7 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled row
 constexpr int kATileBytes = kTileM * 128;  // 16 KB
+constexpr int kTcThreads = 320;            // 10 warps
 
 template <int BLOCK_N>
 struct TcCfg {
@@ -39,7 +41,7 @@ struct TileGeom {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const ConvParams p, const TileGeom g) {
@@ -121,28 +123,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       umma_commit(tmem_full_bar);
     }
   } else {
-    // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) ----
+    // ---- epilogue: warps 2..9 ----
     const int q = warp & 3;
+    constexpr int kHalves = BLOCK_N >= 32 ? 2 : 1;
+    constexpr int kColsPerWarp = BLOCK_N / kHalves;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // tile row = pixel index inside the box
     const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
     const bool valid = (py < p.h) && (px < p.w);
     const int pix = (b * p.h + py) * p.w + px;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (half < kHalves) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
-      if (n0 + c >= p.cout) break;  // warp-uniform
-      uint32_t d0[16], d1[16];
-      tmem_ld16(trow + c, d0);
-      tmem_ld16(trow + BLOCK_N + c, d1);
-      tmem_ld_wait(d0, d1);
-      float v[16];
+      for (int cc = 0; cc < kColsPerWarp; cc += 16) {
+        const int c = half * kColsPerWarp + cc;
+        if (n0 + c >= p.cout) break;  // warp-uniform
+        uint32_t d0[16], d1[16];
+        tmem_ld16(trow + c, d0);
+        tmem_ld16(trow + BLOCK_N + c, d1);
+        tmem_ld_wait(d0, d1);
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
-      if (valid) {
-        epilogue_store<8>(p, pix, n0 + c, v);
-        epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
+        if (valid) {
+          epilogue_store<8>(p, pix, n0 + c, v);
+          epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+        }
       }
     }
   }
@@ -277,7 +285,7 @@ static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap*
     attr_set = true;
   }
   dim3 grid(p.B * g.tiles_x * g.tiles_y, (p.cout + BLOCK_N - 1) / BLOCK_N);
-  conv_tc_kernel<BLOCK_N><<<grid, 192, Cfg::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], p, g);
+  conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, Cfg::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], p, g);
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }

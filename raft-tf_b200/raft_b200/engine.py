@@ -28,6 +28,7 @@ class RaftEngine:
         self.use_graph = use_graph and not os.environ.get("RAFT_B200_NO_GRAPH")
         self.math_mode = math_mode
         torch.backends.cudnn.allow_tf32 = False  # the reference is fp32 end to end
+        torch.backends.cudnn.benchmark = True  # encoders (cuDNN, out of scope): let it pick its best fp32 kernels
         torch.backends.cuda.matmul.allow_tf32 = False
         with torch.cuda.device(self.device):
             self.fnet = Encoder(params, "fnet", small, "instance", self.device)
