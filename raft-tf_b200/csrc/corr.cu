@@ -80,79 +80,126 @@ __global__ void avgpool2_kernel(const float* __restrict__ src, float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// A2/A3  pyramid lookup.  One warp per (query pixel, level):
-//   1. the warp stages the (2r+3)^2 patch of the level that can be touched by the (2r+1)^2 taps
-//      (all taps share one fractional offset; +1 column/row of slack covers fp32 rounding of
-//      cx+dx) into shared memory with index clamping -- row segments are contiguous in HBM;
-//   2. each lane evaluates taps k = lane, lane+32, ... with the reference's exact arithmetic
-//      (utils.py:50-98: trunc-toward-zero, clamp, weights from the clamped x1/y1, add_n order;
-//      __fmul_rn/__fadd_rn keep the compiler from contracting to FMA so results are bit-identical
-//      to the fp32 CPU oracle);
-//   3. the K=(2r+1)^2 results of a level are written contiguously (coalesced).
-// Output either fp32 [pix][4K] (API rb_corr_lookup) or split fp16 planes with a padded channel
-// stride (the layout convc1 consumes).
+// A2/A3  pyramid lookup (model_utils.py:224-249 + utils.py:39-103).
+//
+// A block handles PB = 8 query pixels x 4 levels = 32 "units"; thread = (unit, window row j).
+//   phase 1  the block stages, per unit, the (2r+3) rows x 16 columns of the level that cover every
+//            tap footprint ((2r+1)^2 taps share one fractional offset, +1 row/col of slack for the
+//            fp32 rounding of cx+dx): 16-byte loads from a 4-float-aligned column, row index clamped.
+//   phase 2  thread j of a unit computes the x-side of window column i=j (clamped x0/x1 relative to
+//            the staged columns, qx = x1c - x and 1 - qx) into a small shared table, and keeps the
+//            y-side of its own row j in registers: the separable index math is done once per row /
+//            column instead of once per tap.
+//   phase 3  each thread walks the (2r+1) taps of its row with the reference's exact arithmetic
+//            (trunc toward zero, clamp, weights from the CLAMPED x1/y1, add_n order; __fmul_rn /
+//            __fadd_rn forbid FMA contraction => bit-identical to the fp32 CPU oracle) and stores
+//            channel lvl*K + i*(2r+1) + j: the threads of a unit write consecutive addresses.
+// Output: fp32 [pix][4K] (rb_corr_lookup) or hi/lo fp16 planes with a padded channel stride (the
+// layout convc1 consumes).  r01 profile of the previous one-warp-per-unit kernel: 391 warp
+// instructions per unit, issue-bound (70 % issue slots, 22 % DRAM); this formulation needs ~110.
 // ---------------------------------------------------------------------------------------------
 struct PyramidView {
   const float* base[RB_NUM_LEVELS];
   int hl[RB_NUM_LEVELS], wl[RB_NUM_LEVELS];
+  int vec_ok[RB_NUM_LEVELS];  // level rows are 16-byte aligned (W % 4 == 0 and aligned base)
 };
 
-template <int R, bool SPLIT>
-__global__ void __launch_bounds__(256) corr_lookup_kernel(const __grid_constant__ PyramidView pv, const float2* __restrict__ coords,
-                                                          float* __restrict__ out_f32,
-                                                          __half* __restrict__ out_hi,
-                                                          __half* __restrict__ out_lo, int out_stride,
-                                                          int npix) {
-  constexpr int D = 2 * R + 1, K = D * D, P = D + 2, WARPS = 8;
-  __shared__ float patch[WARPS][P][P + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * WARPS + warp;  // = pix*4 + level
-  const int pix = unit >> 2, lvl = unit & 3;
-  if (pix >= npix) return;
-  const float2 c = __ldg(coords + pix);
-  const float inv = 1.0f / (float)(1 << lvl);
-  const float cx = c.x * inv, cy = c.y * inv;  // centroid / 2**i (model_utils.py:239), exact
-  const int H = pv.hl[lvl], W = pv.wl[lvl];
-  const float* img = pv.base[lvl] + (size_t)pix * H * W;
+constexpr int kLookupPB = 8;    // pixels per block
+constexpr int kPatchCols = 16;  // staged columns per row
+constexpr int kPatchPitch = 20; // floats per staged row (16 + 4 padding: conflict-light column reads)
 
-  // first tap (x_off = y_off = -r) fixes the patch origin
-  const float xf0 = __fadd_rn(cx, (float)(-R)), yf0 = __fadd_rn(cy, (float)(-R));
-  const int bx = min(max((int)xf0, 0), W - 1);
-  const int by = min(max((int)yf0, 0), H - 1);
-  for (int e = lane; e < P * P; e += 32) {
-    int py = e / P, px = e - py * P;
-    int yy = min(by + py, H - 1), xx = min(bx + px, W - 1);
-    patch[warp][py][px] = __ldg(img + (size_t)yy * W + xx);
+template <int R, bool SPLIT>
+__global__ void __launch_bounds__(kLookupPB * 4 * (2 * R + 1))
+corr_lookup_kernel(const __grid_constant__ PyramidView pv, const float2* __restrict__ coords,
+                   float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                   int out_stride, int npix) {
+  constexpr int D = 2 * R + 1, K = D * D, P = D + 2, UNITS = kLookupPB * 4, NT = UNITS * D;
+  __shared__ __align__(16) float patch[UNITS][P][kPatchPitch];
+  __shared__ __align__(16) float4 xtab[UNITS][D];
+  __shared__ int ubase[UNITS][2];  // bx4, by per unit
+  const int tid = threadIdx.x;
+  const int pix0 = blockIdx.x * kLookupPB;
+
+  // ---- phase 0: per-unit origin -------------------------------------------------------------
+  if (tid < UNITS) {
+    const int u = tid, pl = u >> 2, lvl = u & 3;
+    const int pix = min(pix0 + pl, npix - 1);
+    const float2 c = __ldg(coords + pix);
+    const float inv = 1.0f / (float)(1 << lvl);  // centroid / 2**i (model_utils.py:239), exact
+    const int H = pv.hl[lvl], W = pv.wl[lvl];
+    const float xf0 = __fadd_rn(c.x * inv, (float)(-R)), yf0 = __fadd_rn(c.y * inv, (float)(-R));
+    const int bx = min(max((int)xf0, 0), W - 1);
+    ubase[u][0] = bx & ~3;
+    ubase[u][1] = min(max((int)yf0, 0), H - 1);
   }
-  __syncwarp();
+  __syncthreads();
+  // ---- phase 1: stage patches (UNITS * P rows * 4 chunks of 4 floats) -------------------------
+  for (int e = tid; e < UNITS * P * 4; e += NT) {
+    const int u = e / (P * 4), rem = e - u * (P * 4), py = rem >> 2, ch = rem & 3;
+    const int pl = u >> 2, lvl = u & 3;
+    const int pix = min(pix0 + pl, npix - 1);
+    const int H = pv.hl[lvl], W = pv.wl[lvl];
+    const int yy = min(ubase[u][1] + py, H - 1);
+    const int col = ubase[u][0] + ch * 4;
+    const float* row = pv.base[lvl] + ((size_t)pix * H + yy) * W;
+    float4 v;
+    if (pv.vec_ok[lvl]) {
+      v = __ldg(reinterpret_cast<const float4*>(row + col));  // may run past the row end: never indexed
+    } else {
+      v.x = __ldg(row + min(col + 0, W - 1)); v.y = __ldg(row + min(col + 1, W - 1));
+      v.z = __ldg(row + min(col + 2, W - 1)); v.w = __ldg(row + min(col + 3, W - 1));
+    }
+    *reinterpret_cast<float4*>(&patch[u][py][ch * 4]) = v;
+  }
+  // ---- phase 2: separable index math ------------------------------------------------------------
+  const int u = tid / D, j = tid - u * D;
+  const int pl = u >> 2, lvl = u & 3;
+  const int pix = pix0 + pl;
+  const int H = pv.hl[lvl], W = pv.wl[lvl];
+  const float2 c = __ldg(coords + min(pix, npix - 1));
+  const float inv = 1.0f / (float)(1 << lvl);
+  const float cx = c.x * inv, cy = c.y * inv;
+  {
+    // x side of window column i = j (i walks x: model_utils.py:235-237)
+    const float x = __fadd_rn(cx, (float)(j - R));
+    int x0 = (int)x;  // tf.cast truncates toward zero (utils.py:54-57)
+    int x1 = x0 + 1;
+    x0 = min(max(x0, 0), W - 1);
+    x1 = min(max(x1, 0), W - 1);
+    const float qx = __fsub_rn((float)x1, x);  // utils.py:84 (clamped x1)
+    const int bx4 = ubase[u][0];
+    const int ax0 = min(max(x0 - bx4, 0), kPatchCols - 1), ax1 = min(max(x1 - bx4, 0), kPatchCols - 1);
+    xtab[u][j] = make_float4(qx, __fsub_rn(1.0f, qx), __int_as_float(ax0), __int_as_float(ax1));
+  }
+  const float y = __fadd_rn(cy, (float)(j - R));
+  int y0 = (int)y;
+  int y1 = y0 + 1;
+  y0 = min(max(y0, 0), H - 1);
+  y1 = min(max(y1, 0), H - 1);
+  const float qy = __fsub_rn((float)y1, y), pyw = __fsub_rn(1.0f, qy);  // utils.py:85
+  const int by = ubase[u][1];
+  const float* row0 = &patch[u][min(max(y0 - by, 0), P - 1)][0];
+  const float* row1 = &patch[u][min(max(y1 - by, 0), P - 1)][0];
+  __syncthreads();
+  if (pix >= npix) return;
+  // ---- phase 3: taps of window row j ----------------------------------------------------------------
+  const size_t obase = (size_t)pix * out_stride + lvl * K + j;
 #pragma unroll
-  for (int k = lane; k < K; k += 32) {
-    const int i = k / D, j = k - i * D;  // i walks x, j walks y (model_utils.py:235-237)
-    const float x = __fadd_rn(cx, (float)(i - R));
-    const float y = __fadd_rn(cy, (float)(j - R));
-    int x0 = (int)x, y0 = (int)y;  // tf.cast truncates toward zero (utils.py:54-57)
-    int x1 = x0 + 1, y1 = y0 + 1;
-    x0 = min(max(x0, 0), W - 1); x1 = min(max(x1, 0), W - 1);
-    y0 = min(max(y0, 0), H - 1); y1 = min(max(y1, 0), H - 1);
-    const float qx = __fsub_rn((float)x1, x), qy = __fsub_rn((float)y1, y);  // utils.py:84-85
-    const float pxw = __fsub_rn(1.0f, qx), pyw = __fsub_rn(1.0f, qy);
-    const float wa = __fmul_rn(qx, qy), wb = __fmul_rn(qx, pyw);
-    const float wc = __fmul_rn(pxw, qy), wd = __fmul_rn(pxw, pyw);
-    // indices relative to the staged patch; clamp keeps pathological coords in range
-    const int ax0 = min(max(x0 - bx, 0), P - 1), ax1 = min(max(x1 - bx, 0), P - 1);
-    const int ay0 = min(max(y0 - by, 0), P - 1), ay1 = min(max(y1 - by, 0), P - 1);
-    const float Ia = patch[warp][ay0][ax0], Ib = patch[warp][ay1][ax0];
-    const float Ic = patch[warp][ay0][ax1], Id = patch[warp][ay1][ax1];
-    float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
-                        __fmul_rn(wd, Id));  // tf.add_n order (utils.py:98)
+  for (int i = 0; i < D; ++i) {
+    const float4 xt = xtab[u][i];
+    const int ax0 = __float_as_int(xt.z), ax1 = __float_as_int(xt.w);
+    const float wa = __fmul_rn(xt.x, qy), wb = __fmul_rn(xt.x, pyw);  // utils.py:86-89
+    const float wc = __fmul_rn(xt.y, qy), wd = __fmul_rn(xt.y, pyw);
+    const float Ia = row0[ax0], Ib = row1[ax0], Ic = row0[ax1], Id = row1[ax1];
+    const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
+                              __fmul_rn(wd, Id));  // tf.add_n order (utils.py:98)
     if constexpr (SPLIT) {
       __half hi, lo;
       split_f32(v, hi, lo);
-      size_t o = (size_t)pix * out_stride + lvl * K + k;
-      out_hi[o] = hi;
-      out_lo[o] = lo;
+      out_hi[obase + i * D] = hi;
+      out_lo[obase + i * D] = lo;
     } else {
-      out_f32[(size_t)pix * out_stride + lvl * K + k] = v;
+      out_f32[obase + i * D] = v;
     }
   }
 }
@@ -190,6 +237,7 @@ int pyramid_view(const float* pyramid, int B, int h, int w, PyramidView* pv) {
     pv->base[l] = pyramid + off;
     pv->hl[l] = hl;
     pv->wl[l] = wl;
+    pv->vec_ok[l] = (wl % 4 == 0) && (reinterpret_cast<uintptr_t>(pyramid + off) % 16 == 0);
     off += rows * hl * wl;
   }
   return RB_OK;
@@ -201,14 +249,15 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
   int rc = pyramid_view(pyramid, B, h, w, &pv);
   if (rc) return rc;
   int npix = B * h * w;
-  int units = npix * 4;
-  dim3 grid((units + 7) / 8), block(256);
+  dim3 grid((npix + kLookupPB - 1) / kLookupPB);
   const float2* c2 = reinterpret_cast<const float2*>(coords);
   bool split = out_hi != nullptr;
   if (radius == 4) {
+    dim3 block(kLookupPB * 4 * 9);
     if (split) corr_lookup_kernel<4, true><<<grid, block, 0, s>>>(pv, c2, nullptr, out_hi, out_lo, out_stride, npix);
     else corr_lookup_kernel<4, false><<<grid, block, 0, s>>>(pv, c2, out_f32, nullptr, nullptr, out_stride, npix);
   } else if (radius == 3) {
+    dim3 block(kLookupPB * 4 * 7);
     if (split) corr_lookup_kernel<3, true><<<grid, block, 0, s>>>(pv, c2, nullptr, out_hi, out_lo, out_stride, npix);
     else corr_lookup_kernel<3, false><<<grid, block, 0, s>>>(pv, c2, out_f32, nullptr, nullptr, out_stride, npix);
   } else {
@@ -252,7 +301,7 @@ extern "C" int rb_corr_pyramid_bytes(int B, int h, int w, size_t* bytes) {
              "rb_corr_pyramid_bytes: grid %dx%d too small for 4 levels", h, w);
   size_t off;
   rb_corr_level_offset(B, h, w, RB_NUM_LEVELS, &off, nullptr, nullptr);
-  *bytes = off * sizeof(float);
+  *bytes = off * sizeof(float) + 256;  // tail padding: the lookup stages 16-column row segments with vector loads
   return RB_OK;
 }
 

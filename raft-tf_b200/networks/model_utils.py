@@ -59,7 +59,9 @@ def GetCorrPyramid(fmap1, fmap2, num_levels=4):
 def _as_buffer(corr_pyramid):
     if isinstance(corr_pyramid, CorrPyramid) and corr_pyramid.buffer is not None:
         return corr_pyramid.buffer
-    return torch.cat([t.reshape(-1).float() for t in corr_pyramid]).contiguous()
+    parts = [t.reshape(-1).float() for t in corr_pyramid]
+    parts.append(torch.zeros(64, dtype=torch.float32, device=parts[0].device))  # tail padding (rb_corr_pyramid_bytes)
+    return torch.cat(parts).contiguous()
 
 
 def SampleCorr(corr_pyramid, coords, num_levels=4, radius=4):

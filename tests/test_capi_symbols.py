@@ -30,7 +30,7 @@ def test_host_only_queries():
     assert lib.rb_update_conv_name(0, 5) == b"update_block/gru/convz1"
     assert lib.rb_update_conv_name(1, 8) == b"update_block/flow_head/conv2"
     # pyramid size at things@440x1024 = 261.3 MB
-    assert capi.size_query(lib.rb_corr_pyramid_bytes, 1, 55, 128) == 4 * 7040 * (55 * 128 + 27 * 64 + 13 * 32 + 6 * 16)
+    assert capi.size_query(lib.rb_corr_pyramid_bytes, 1, 55, 128) == 4 * 7040 * (55 * 128 + 27 * 64 + 13 * 32 + 6 * 16) + 256
     # error path: status code + message, no abort
     out = ctypes.c_size_t()
     assert lib.rb_corr_pyramid_bytes(1, 4, 4, ctypes.byref(out)) == -1

@@ -61,7 +61,7 @@ def test_lookup_split_output_matches_fp32(cuda):
     B, h, w, r = 1, 16, 32, 4
     pyr = _rand_pyramid(B, h, w, 7)
     coords = _coords(B, h, w, 9).to(cuda)
-    buf = torch.cat([p.reshape(-1) for p in pyr]).to(cuda)
+    buf = torch.cat([p.reshape(-1) for p in pyr] + [torch.zeros(64)]).to(cuda)
     ref = O.sample_corr(pyr, coords.cpu(), radius=r)
     lib = capi.lib
     wsb = capi.size_query(lib.rb_update_workspace_bytes, 0, B, h, w)
