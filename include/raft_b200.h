@@ -107,6 +107,10 @@ int rb_update_workspace_bytes(int small, int B, int h, int w, size_t* bytes);
  * already activated: net [B,h,w,hidden], inp [B,h,w,context]. */
 int rb_update_set_state(int small, void* workspace, const float* net, const float* inp, int B,
                         int h, int w, void* stream);
+/* Same from the raw context-encoder output cnet [B,h,w,hidden+context]: applies the split, tanh and relu of
+ * RAFT.py:85-87 itself. */
+int rb_update_set_state_cnet(int small, void* workspace, const float* cnet, int B, int h, int w,
+                             void* stream);
 int rb_update_get_net(int small, const void* workspace, float* net, int B, int h, int w,
                       void* stream);
 /* Lookup written straight into the workspace in the layout the first conv consumes (fast path). */
@@ -130,6 +134,25 @@ int rb_upsample_convex(const float* coords1, const float* mask, float* out, int 
                        void* stream);
 /* scale = 1.0 reproduces the reference (no x8, utils.py:110); upstream RAFT would pass 8.0. */
 int rb_upflow8(const float* coords1, float* out, int B, int h, int w, float scale, void* stream);
+
+/* ---- F1: BasicEncoder / SmallEncoder  networks/model_utils.py:61-105 (+ input_preprocess RAFT.py:53-59) --
+ * norm: 0 = 'none', 1 = 'instance' (fnet), 2 = 'batch' (cnet of raft-things; folded into the convs at pack
+ * time from inference statistics).  Convs are enumerated in execution order; names are relative to the
+ * encoder scope ("conv1", "layer2/0/downsample.0", ...), rb_encoder_norm_name gives the scope of the norm
+ * that follows conv i ("" = none).  W_host[i] HWIO fp32, b_host[i] [cout]; bn_host[i] (norm == 2 only) is
+ * [gamma | beta | mean/EMA | variance/EMA], 4*cout floats.  image: [B,H,W,3] fp32 in [0,1] (2x-1 is applied
+ * inside); out: [B,ceil(H/8),ceil(W/8),out_dim] fp32.  The workspace must be zero-filled once before first use. */
+int rb_encoder_num_convs(int small);
+const char* rb_encoder_conv_name(int small, int i);
+const char* rb_encoder_norm_name(int small, int i);
+int rb_encoder_conv_shape(int small, int i, int out_dim, int* k, int* stride, int* cin, int* cout);
+int rb_encoder_weights_bytes(int small, int out_dim, size_t* bytes);
+int rb_encoder_weights_pack(int small, int norm, int out_dim, const float* const* W_host,
+                            const float* const* b_host, const float* const* bn_host, void* blob,
+                            size_t blob_bytes, void* stream);
+int rb_encoder_workspace_bytes(int small, int B, int H, int W, size_t* bytes);
+int rb_encoder_forward(int small, int norm, const void* weights, const float* image, float* out, int B,
+                       int H, int W, int out_dim, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -168,6 +168,28 @@ __global__ void set_state_kernel(const float* __restrict__ net, const float* __r
   }
 }
 
+// net = tanh(cnet[..., :hidden]), inp = relu(cnet[..., hidden:])  (RAFT.py:85-87)
+__global__ void set_state_cnet_kernel(const float* __restrict__ cnet, Workspace W, int npix, int hidden, int ctx, int hx) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int per = hidden + ctx;
+  if (i >= (size_t)npix * per) return;
+  int pix = i / per, c = i % per;
+  float v = cnet[i];
+  __half hi, lo;
+  size_t o = (size_t)pix * hx + c;
+  if (c < hidden) {
+    v = tanhf(v);
+    W.H[(size_t)pix * hidden + c] = v;
+    split_f32(v, hi, lo);
+    W.hx.hi[o] = hi; W.hx.lo[o] = lo;
+  } else {
+    v = fmaxf(v, 0.f);
+    split_f32(v, hi, lo);
+    W.hx.hi[o] = hi; W.hx.lo[o] = lo;
+    W.qx.hi[o] = hi; W.qx.lo[o] = lo;
+  }
+}
+
 __global__ void set_corr_kernel(const float* __restrict__ corr, SplitPtr dst, int npix, int ch, int stride) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)npix * ch) return;
@@ -439,6 +461,19 @@ extern "C" int rb_update_set_state(int small, void* workspace, const float* net,
   set_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(net, inp, W, (int)npix, v.hidden,
                                                                                   v.ctx, v.hx);
   RB_CHECK_LAUNCH("set_state_kernel");
+  return RB_OK;
+}
+
+extern "C" int rb_update_set_state_cnet(int small, void* workspace, const float* cnet, int B, int h, int w, void* stream) {
+  RB_REQUIRE(workspace && cnet, RB_ERR_BAD_ARG, "rb_update_set_state_cnet: null pointer");
+  int rc = check_shape("rb_update_set_state_cnet", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  size_t npix = (size_t)B * h * w;
+  Workspace W = workspace_layout(v, npix, workspace);
+  size_t n = npix * (v.hidden + v.ctx);
+  set_state_cnet_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cnet, W, (int)npix, v.hidden, v.ctx, v.hx);
+  RB_CHECK_LAUNCH("set_state_cnet_kernel");
   return RB_OK;
 }
 

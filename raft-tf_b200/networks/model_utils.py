@@ -113,3 +113,27 @@ def SmallUpdateBlock(net, inp, corr, flow, name="update_block", hidden_dim=96):
     """model_utils.py:187-194 -> (net, None, delta_flow)."""
     assert name == "update_block" and hidden_dim == 96
     return _update_block(True, net, inp, corr, flow, False)
+
+
+# ---- encoders (model_utils.py:61-105) -----------------------------------------------------------
+_ENC = {}
+
+
+def _encoder(name, small, norm_fn, out_dim, device):
+    from raft_b200.encoders import CudaEncoder
+    key = (name, bool(small), norm_fn, int(out_dim), str(device), id(_VARS["params"]))
+    if key not in _ENC:
+        if _VARS["params"] is None:
+            raise RuntimeError("networks.model_utils.set_variables(params) has not been called")
+        _ENC[key] = CudaEncoder(_VARS["params"], name, small, norm_fn, out_dim, device)
+    return _ENC[key]
+
+
+def BasicEncoder(inputs, name, output_dim=256, norm_fn='instance', dropout=0.0):
+    """model_utils.py:61-82.  ``inputs``: [B,H,W,3] in [-1,1] (already through input_preprocess, RAFT.py:53-59)."""
+    return _encoder(name, False, norm_fn, output_dim, inputs.device)((inputs + 1.0) * 0.5)
+
+
+def SmallEncoder(inputs, name, out_dim, norm_fn='batch', dropout=0.0):
+    """model_utils.py:84-105."""
+    return _encoder(name, True, norm_fn, out_dim, inputs.device)((inputs + 1.0) * 0.5)

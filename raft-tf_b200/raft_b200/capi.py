@@ -42,6 +42,7 @@ SIGNATURES = {
     "rb_update_weights_pack": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _vp]),
     "rb_update_workspace_bytes": (_i, [_i, _i, _i, _i, _psz]),
     "rb_update_set_state": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rb_update_set_state_cnet": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_get_net": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_lookup": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_set_corr": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
@@ -49,6 +50,14 @@ SIGNATURES = {
     "rb_raft_iterate": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rb_upsample_convex": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_upflow8": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
+    "rb_encoder_num_convs": (_i, [_i]),
+    "rb_encoder_conv_name": (C.c_char_p, [_i, _i]),
+    "rb_encoder_norm_name": (C.c_char_p, [_i, _i]),
+    "rb_encoder_conv_shape": (_i, [_i, _i, _i, _pi, _pi, _pi, _pi]),
+    "rb_encoder_weights_bytes": (_i, [_i, _i, _psz]),
+    "rb_encoder_weights_pack": (_i, [_i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _vp]),
+    "rb_encoder_workspace_bytes": (_i, [_i, _i, _i, _i, _psz]),
+    "rb_encoder_forward": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = the library does not export a declared symbol

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .encoders import Encoder
+from .encoders import CudaEncoder, Encoder
 from .weights import pack_update_block
 
 
@@ -30,9 +30,16 @@ class RaftEngine:
         torch.backends.cudnn.allow_tf32 = False  # the reference is fp32 end to end
         torch.backends.cudnn.benchmark = True  # encoders (cuDNN, out of scope): let it pick its best fp32 kernels
         torch.backends.cuda.matmul.allow_tf32 = False
+        # encoders: raft_b200's own kernels by default; RAFT_B200_TORCH_ENCODERS=1 selects the torch/cuDNN restatement
+        self.torch_encoders = bool(os.environ.get("RAFT_B200_TORCH_ENCODERS"))
+        cnorm = "none" if small else "batch"
         with torch.cuda.device(self.device):
-            self.fnet = Encoder(params, "fnet", small, "instance", self.device)
-            self.cnet = Encoder(params, "cnet", small, "none" if small else "batch", self.device)
+            if self.torch_encoders:
+                self.fnet = Encoder(params, "fnet", small, "instance", self.device)
+                self.cnet = Encoder(params, "cnet", small, cnorm, self.device)
+            else:
+                self.fnet = CudaEncoder(params, "fnet", small, "instance", self.fdim, self.device)
+                self.cnet = CudaEncoder(params, "cnet", small, cnorm, self.hidden + self.ctx, self.device)
             self.blob = pack_update_block(params, small, self.device)
         self._shape = None
         self._graph = None
@@ -57,24 +64,24 @@ class RaftEngine:
         self.coords1 = torch.empty(B, h, w, 2, dtype=torch.float32, device=d)
         self.mask = None if self.small else torch.empty(B, h, w, 576, dtype=torch.float32, device=d)
         self.flow_up = torch.empty(B, H, W, 2, dtype=torch.float32, device=d)
-        self.net_in = torch.empty(B, h, w, self.hidden, dtype=torch.float32, device=d)
-        self.inp_in = torch.empty(B, h, w, self.ctx, dtype=torch.float32, device=d)
-        self.fmap1 = torch.empty(B, h, w, self.fdim, dtype=torch.float32, device=d)
-        self.fmap2 = torch.empty(B, h, w, self.fdim, dtype=torch.float32, device=d)
+        self.fmaps = torch.empty(2 * B, h, w, self.fdim, dtype=torch.float32, device=d)
+        self.fmap1, self.fmap2 = self.fmaps[:B], self.fmaps[B:]
+        self.cmap = torch.empty(B, h, w, self.hidden + self.ctx, dtype=torch.float32, device=d)
+        self.images = torch.empty(2 * B, H, W, 3, dtype=torch.float32, device=d)  # [left | right], [0,1]
         self._shape = (B, H, W)
         self._graph = None
 
     # ---- stages --------------------------------------------------------------------------------
-    def encode(self, left: torch.Tensor, right: torch.Tensor):
-        """RAFT.py:53-59,79-87: 2x-1, fnet(left), fnet(right), cnet(left) -> split/tanh/relu."""
-        B = left.shape[0]
-        both = torch.cat([left, right], 0) * 2.0 - 1.0
-        fm = self.fnet(both)  # instance norm is per sample, so batching left|right is exact
-        self.fmap1.copy_(fm[:B])
-        self.fmap2.copy_(fm[B:])
-        c = self.cnet(both[:B])
-        self.net_in.copy_(torch.tanh(c[..., :self.hidden]))
-        self.inp_in.copy_(torch.relu(c[..., self.hidden:]))
+    def encode(self):
+        """RAFT.py:53-59,79-87 on self.images = [left | right]: 2x-1, fnet(left), fnet(right), cnet(left)."""
+        B = self._shape[0]
+        if self.torch_encoders:
+            both = self.images * 2.0 - 1.0
+            self.fmaps.copy_(self.fnet(both))  # instance norm is per sample, so batching left|right is exact
+            self.cmap.copy_(self.cnet(both[:B]))
+        else:
+            self.fnet(self.images, out=self.fmaps)
+            self.cnet(self.images[:B], out=self.cmap)
 
     def _hot_path(self):
         """corr build + iterations + upsampling: hand-written kernels only (graph-capturable)."""
@@ -83,7 +90,7 @@ class RaftEngine:
         capi.check(lib.rb_set_math_mode(self.math_mode))
         capi.check(lib.rb_corr_build(capi.ptr(self.fmap1), capi.ptr(self.fmap2), capi.ptr(self.pyramid), B, h, w,
                                      self.fdim, capi.ptr(self.corr_ws), self.cws_bytes, st))
-        capi.check(lib.rb_update_set_state(s, capi.ptr(self.ws), capi.ptr(self.net_in), capi.ptr(self.inp_in), B, h, w, st))
+        capi.check(lib.rb_update_set_state_cnet(s, capi.ptr(self.ws), capi.ptr(self.cmap), B, h, w, st))
         capi.check(lib.rb_coords_grid(capi.ptr(self.coords1), B, h, w, st))
         capi.check(lib.rb_raft_iterate(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.pyramid),
                                        capi.ptr(self.coords1), capi.ptr(self.mask), B, h, w, self.iters, st))
@@ -93,24 +100,35 @@ class RaftEngine:
             capi.check(lib.rb_upsample_convex(capi.ptr(self.coords1), capi.ptr(self.mask), capi.ptr(self.flow_up),
                                               B, h, w, st))
 
+    def _all(self):
+        self.encode()
+        self._hot_path()
+
     def launches_per_forward(self) -> int:
-        """Number of raft_b200 kernels one hot-path pass launches (counted by the library)."""
+        """Number of raft_b200 kernels one forward pass launches (counted by the library; torch kernels of
+        the optional cuDNN encoder path are not included)."""
         capi.lib.rb_launch_count_reset()
         with torch.cuda.device(self.device):
-            self._hot_path()
+            self._all()
             torch.cuda.synchronize()
         return int(capi.lib.rb_launch_count())
 
-    def run_hot_path(self):
+    def run(self):
+        """encoders + hot path on self.images; replayed from one CUDA graph when every stage is ours."""
         if not self.use_graph:
-            self._hot_path()
+            self._all()
             return
+        if self.torch_encoders:  # cuDNN autotuning does not belong in a capture: graph only the hot path
+            self.encode()
+            body = self._hot_path
+        else:
+            body = self._all
         if self._graph is None:
-            self._hot_path()  # warm-up: function attributes, tensor-map cache
+            body()  # warm-up: function attributes, tensor-map cache
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._hot_path()
+                body()
             self._graph = g
         self._graph.replay()
 
@@ -120,9 +138,11 @@ class RaftEngine:
         [B,H,W,2] flow (a view of an engine-owned buffer, overwritten by the next call)."""
         assert left.shape == right.shape and left.dim() == 4 and left.shape[-1] == 3
         with torch.cuda.device(self.device):
-            self._ensure(left.shape[0], left.shape[1], left.shape[2])
-            self.encode(left.float(), right.float())
-            self.run_hot_path()
+            B = left.shape[0]
+            self._ensure(B, left.shape[1], left.shape[2])
+            self.images[:B].copy_(left, non_blocking=True)  # H2D when the caller hands pinned host tensors
+            self.images[B:].copy_(right, non_blocking=True)
+            self.run()
         return self.flow_up
 
     def lowres_flow(self) -> torch.Tensor:

@@ -218,3 +218,29 @@ def test_error_paths_do_not_abort(cuda):
     assert lib.rb_corr_lookup(capi.ptr(t), capi.ptr(t), capi.ptr(t), 1, 8, 8, 5, capi.stream()) == -3
     assert b"radius" in lib.rb_last_error()
     assert lib.rb_corr_build(None, None, None, 1, 8, 8, 256, None, 0, None) == -2
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("small,name,norm,out_dim,B,H,W", [
+    (False, "fnet", "instance", 256, 2, 64, 96), (False, "cnet", "batch", 256, 1, 72, 104),
+    (True, "fnet", "instance", 128, 2, 64, 96), (True, "cnet", "none", 160, 1, 72, 104)])
+def test_encoder(cuda, mode, small, name, norm, out_dim, B, H, W):
+    """BasicEncoder / SmallEncoder (model_utils.py:61-105) on raft_b200's own kernels vs the fp64 oracle:
+    asymmetric TF 'SAME' padding on the stride-2 convs, instance norm / folded batch norm / no norm."""
+    from raft_b200 import capi, synth
+    from raft_b200.encoders import CudaEncoder
+    p = synth.make_weights(small)
+    g = torch.Generator().manual_seed(31)
+    img = torch.rand(B, H, W, 3, generator=g)
+    pt = {k: torch.from_numpy(v).double() for k, v in p.items()}
+    enc = O.small_encoder if small else O.basic_encoder
+    ref = enc(2.0 * img.double() - 1.0, pt, name, norm)
+    capi.check(capi.lib.rb_set_math_mode(dict(_modes())[mode]))
+    try:
+        out = CudaEncoder(p, name, small, norm, out_dim, cuda)(img.to(cuda))
+        torch.cuda.synchronize()
+    finally:
+        capi.lib.rb_set_math_mode(capi.RB_MATH_TC)
+    assert out.shape == ref.shape
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 1e-4 * max(ref.abs().max().item(), 1.0), f"max abs err {err:.3e} (scale {ref.abs().max():.2f})"

@@ -1,0 +1,54 @@
+"""Micro-benchmark / profiling driver for single kernels (run under gpurun, optionally under ncu).
+usage: python tools/micro.py lookup|update|corr [--B 1] [--reps 5]"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "raft-tf_b200"))
+import torch
+from raft_b200 import capi, synth
+from raft_b200.weights import pack_update_block
+
+ap = argparse.ArgumentParser()
+ap.add_argument("what")
+ap.add_argument("--B", type=int, default=1)
+ap.add_argument("--h", type=int, default=55)
+ap.add_argument("--w", type=int, default=128)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--small", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+lib, B, h, w, s = capi.lib, a.B, a.h, a.w, int(a.small)
+r = 3 if a.small else 4
+g = torch.Generator(device="cpu").manual_seed(1234)
+pyr_bytes = capi.size_query(lib.rb_corr_pyramid_bytes, B, h, w)
+pyr = torch.randn(pyr_bytes // 4, device=dev)
+grid = torch.stack(torch.meshgrid(torch.arange(w), torch.arange(h), indexing="xy"), -1).float()[None].repeat(B, 1, 1, 1)
+coords = (grid + (torch.rand(B, h, w, 2, generator=g) * 16 - 8)).to(dev).contiguous()
+wsb = capi.size_query(lib.rb_update_workspace_bytes, s, B, h, w)
+ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+st = None
+if a.what == "lookup":
+    fn = lambda: capi.check(lib.rb_update_lookup(s, capi.ptr(ws), capi.ptr(pyr), capi.ptr(coords), B, h, w, capi.stream()))
+elif a.what == "update":
+    blob = pack_update_block(synth.make_weights(a.small), a.small, dev)
+    hid, ctx = (96, 64) if a.small else (128, 128)
+    net = torch.tanh(torch.randn(B, h, w, hid, device=dev)); inp = torch.relu(torch.randn(B, h, w, ctx, device=dev))
+    capi.check(lib.rb_update_set_state(s, capi.ptr(ws), capi.ptr(net), capi.ptr(inp), B, h, w, capi.stream()))
+    capi.check(lib.rb_update_lookup(s, capi.ptr(ws), capi.ptr(pyr), capi.ptr(coords), B, h, w, capi.stream()))
+    c1 = coords.clone()
+    fn = lambda: capi.check(lib.rb_update_step(s, capi.ptr(blob), capi.ptr(ws), capi.ptr(c1), None, None, B, h, w, capi.stream()))
+else:
+    raise SystemExit("unknown")
+for _ in range(a.reps):
+    fn()
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+gr = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gr):
+    for _ in range(20):
+        fn()
+gr.replay(); torch.cuda.synchronize()
+ev[0].record(); gr.replay(); ev[1].record(); torch.cuda.synchronize()
+print(f"{a.what}: {ev[0].elapsed_time(ev[1]) / 20 * 1e3:.2f} us per call (L2 warm, graph of 20)")
