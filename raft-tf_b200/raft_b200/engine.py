@@ -75,6 +75,7 @@ class RaftEngine:
     def encode(self):
         """RAFT.py:53-59,79-87 on self.images = [left | right]: 2x-1, fnet(left), fnet(right), cnet(left)."""
         B = self._shape[0]
+        capi.check(capi.lib.rb_set_math_mode(self.math_mode))  # per-thread library state: set before ANY kernel of ours
         if self.torch_encoders:
             both = self.images * 2.0 - 1.0
             self.fmaps.copy_(self.fnet(both))  # instance norm is per sample, so batching left|right is exact
