@@ -26,11 +26,15 @@ constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled
 constexpr int kATileBytes = kTileM * 128;  // 16 KB
 constexpr int kTcThreads = 320;            // 10 warps
 
-template <int BLOCK_N>
+// SHALLOW = 2 pipeline stages and two CTAs per SM: for convs with many pixel tiles and a short K loop
+// (the encoder layers) the epilogue of one CTA overlaps the MMA loop of its neighbour.  Otherwise
+// one CTA per SM with as many stages as fit (the single-wave, long-K convs of the update block).
+template <int BLOCK_N, bool SHALLOW>
 struct TcCfg {
   static constexpr int kBTileBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 4 ? 4 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = SHALLOW ? 2 : ((200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes);
+  static constexpr int kMinBlocks = SHALLOW ? 2 : 1;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -40,12 +44,12 @@ struct TileGeom {
   int tiles_x, tiles_y;  // per image
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BLOCK_N, bool SHALLOW>
+__global__ void __launch_bounds__(kTcThreads, (TcCfg<BLOCK_N, SHALLOW>::kMinBlocks))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const ConvParams p, const TileGeom g) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -275,17 +279,17 @@ static int choose_block_n(int cout, long m_tiles) {
   return best;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool SHALLOW>
 static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap* maps, cudaStream_t s) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
   static bool attr_set = false;
   if (!attr_set) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, SHALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
   dim3 grid(p.B * g.tiles_x * g.tiles_y, (p.cout + BLOCK_N - 1) / BLOCK_N);
-  conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, Cfg::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], p, g);
+  conv_tc_kernel<BLOCK_N, SHALLOW><<<grid, kTcThreads, Cfg::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], p, g);
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
@@ -314,12 +318,15 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
     if ((rc = cached_tmap(&maps[2], p.w_hi, 3, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
   }
+  const long ctas = m_tiles * ((p.cout + bn - 1) / bn);
+  const int kiters = p.kh * p.kw * (p.cin_pad / kChunkK);
+  const bool shallow = bn <= 64 && ctas > 2 * 148 && kiters <= 18;
   switch (bn) {
-    case 16: return launch_cfg<16>(p, g, maps, s);
-    case 32: return launch_cfg<32>(p, g, maps, s);
-    case 64: return launch_cfg<64>(p, g, maps, s);
-    case 96: return launch_cfg<96>(p, g, maps, s);
-    default: return launch_cfg<128>(p, g, maps, s);
+    case 16: return shallow ? launch_cfg<16, true>(p, g, maps, s) : launch_cfg<16, false>(p, g, maps, s);
+    case 32: return shallow ? launch_cfg<32, true>(p, g, maps, s) : launch_cfg<32, false>(p, g, maps, s);
+    case 64: return shallow ? launch_cfg<64, true>(p, g, maps, s) : launch_cfg<64, false>(p, g, maps, s);
+    case 96: return launch_cfg<96, false>(p, g, maps, s);
+    default: return launch_cfg<128, false>(p, g, maps, s);
   }
 }
 

@@ -129,6 +129,61 @@ __global__ void enc_gather_kernel(const float* __restrict__ img, const __half* _
   out_lo[i] = lo;
 }
 
+// Stem gather (7x7 stride 2 over the 3-channel image): 8 consecutive k per thread, 16-byte stores.
+__global__ void enc_gather_img8_kernel(const float* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                       int B, int H, int W, int cin, int k, int s, int pt, int pl, int oh, int ow, int kpad) {
+  const int K = k * k * cin, k8 = kpad / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * oh * ow * k8) return;
+  const int kk0 = (i % k8) * 8;
+  size_t px = i / k8;
+  const int ox = px % ow, oy = (px / ow) % oh, b = px / ((size_t)ow * oh);
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kk = kk0 + j;
+    float v = 0.f;
+    bool in = false;
+    if (kk < K) {
+      const int ci = kk % cin, t = kk / cin, kx = t % k, ky = t / k;
+      const int iy = oy * s + ky - pt, ix = ox * s + kx - pl;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        v = 2.0f * __ldg(img + ((size_t)(b * H + iy) * W + ix) * cin + ci) - 1.0f;  // RAFT.py:53-59
+        in = true;
+      }
+    }
+    if (in) split_f32(v, hi[j], lo[j]);
+    else hi[j] = lo[j] = __float2half_rn(0.f);  // SAME zero padding is applied AFTER the 2x-1 preprocessing
+  }
+  *reinterpret_cast<uint4*>(out_hi + px * kpad + kk0) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out_lo + px * kpad + kk0) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// Same gather for split sources whose channel count is a multiple of 8: one thread moves 8 channels
+// (16 bytes per plane) -- the 3x3/1x1 stride-2 convs of layer2/layer3.
+__global__ void enc_gather8_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_stride,
+                                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W, int cin,
+                                   int k, int s, int pt, int pl, int oh, int ow, int kpad) {
+  const int K = k * k * cin, k8 = kpad / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * oh * ow * k8) return;
+  const int kk = (i % k8) * 8;
+  size_t px = i / k8;
+  uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+  if (kk < K) {
+    const int ci = kk % cin, t = kk / cin, kx = t % k, ky = t / k;
+    const int ox = px % ow, oy = (px / ow) % oh, b = px / ((size_t)ow * oh);
+    const int iy = oy * s + ky - pt, ix = ox * s + kx - pl;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      size_t src = ((size_t)(b * H + iy) * W + ix) * in_stride + ci;
+      hi = *reinterpret_cast<const uint4*>(in_hi + src);
+      lo = *reinterpret_cast<const uint4*>(in_lo + src);
+    }
+  }
+  *reinterpret_cast<uint4*>(out_hi + px * kpad + kk) = hi;
+  *reinterpret_cast<uint4*>(out_lo + px * kpad + kk) = lo;
+}
+
 // instance-norm statistics, stage 1: per (sample, pixel strip) partial sum / sum of squares per channel
 __global__ void inorm_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int npx, int C, int strips) {
   const int b = blockIdx.y, strip = blockIdx.x, c = threadIdx.x % C, lane_px = threadIdx.x / C;
@@ -151,51 +206,76 @@ __global__ void inorm_partial_kernel(const float* __restrict__ x, double* __rest
     part[(((size_t)b * strips + strip) * 2 + 1) * C + c] = s2;
   }
 }
-// stage 2: mean and 1/sqrt(var+eps) (biased variance, eps 1e-5: tensorpack InstanceNorm)
+// stage 2: mean and 1/sqrt(var+eps) (biased variance, eps 1e-5: tensorpack InstanceNorm).
+// One block per (sample, channel): the strips are summed by a fixed-shape tree (deterministic).
 __global__ void inorm_final_kernel(const double* __restrict__ part, float2* __restrict__ stat, int npx, int C, int strips) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, s2 = 0.0;
-  for (int t = 0; t < strips; ++t) {
-    s += part[(((size_t)b * strips + t) * 2 + 0) * C + c];
-    s2 += part[(((size_t)b * strips + t) * 2 + 1) * C + c];
+  const int b = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
+  __shared__ double s1[256], s2[256];
+  double a = 0.0, q = 0.0;
+  for (int k = t; k < strips; k += 256) {
+    a += part[(((size_t)b * strips + k) * 2 + 0) * C + c];
+    q += part[(((size_t)b * strips + k) * 2 + 1) * C + c];
   }
-  const double mean = s / npx;
-  const double var = fmax(s2 / npx - mean * mean, 0.0);
-  stat[b * C + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+  s1[t] = a; s2[t] = q;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) { s1[t] += s1[t + w]; s2[t] += s2[t + w]; }
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double mean = s1[0] / npx;
+    const double var = fmax(s2[0] / npx - mean * mean, 0.0);
+    stat[b * C + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+  }
 }
-// y = (x-mean)*rstd [ReLU]; optionally out = relu(res + y) (ResidualBlock :31-35); -> split [px][Cpad]
+// y = (x-mean)*rstd [ReLU]; optionally out = relu(res + y) (ResidualBlock :31-35); -> split [px][Cpad].
+// 8 channels per thread (C is a multiple of 8 for every encoder layer).
 __global__ void inorm_apply_kernel(const float* __restrict__ x, const float2* __restrict__ stat, const __half* __restrict__ res_hi,
                                    const __half* __restrict__ res_lo, int res_stride, __half* __restrict__ out_hi,
                                    __half* __restrict__ out_lo, int out_stride, int B, int npx, int C, int relu) {
+  const int c8 = C / 8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * npx * C) return;
-  const int c = i % C;
-  const size_t px = i / C;
+  if (i >= (size_t)B * npx * c8) return;
+  const int c = (i % c8) * 8;
+  const size_t px = i / c8;
   const int b = px / npx;
-  const float2 st = stat[b * C + c];
-  float y = (x[i] - st.x) * st.y;
-  if (relu) y = fmaxf(y, 0.f);
-  if (res_hi) y = fmaxf(join_f32(res_hi[px * res_stride + c], res_lo[px * res_stride + c]) + y, 0.f);
-  __half hi, lo;
-  split_f32(y, hi, lo);
-  out_hi[px * out_stride + c] = hi;
-  out_lo[px * out_stride + c] = lo;
+  const float4 x0 = *reinterpret_cast<const float4*>(x + px * C + c), x1 = *reinterpret_cast<const float4*>(x + px * C + c + 4);
+  float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  __align__(16) __half rh[8], rl[8];
+  if (res_hi) {
+    *reinterpret_cast<uint4*>(rh) = *reinterpret_cast<const uint4*>(res_hi + px * res_stride + c);
+    *reinterpret_cast<uint4*>(rl) = *reinterpret_cast<const uint4*>(res_lo + px * res_stride + c);
+  }
+  __align__(16) __half oh[8], ol[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float2 st = stat[b * C + c + k];
+    float y = (v[k] - st.x) * st.y;
+    if (relu) y = fmaxf(y, 0.f);
+    if (res_hi) y = fmaxf(join_f32(rh[k], rl[k]) + y, 0.f);
+    split_f32(y, oh[k], ol[k]);
+  }
+  *reinterpret_cast<uint4*>(out_hi + px * out_stride + c) = *reinterpret_cast<const uint4*>(oh);
+  *reinterpret_cast<uint4*>(out_lo + px * out_stride + c) = *reinterpret_cast<const uint4*>(ol);
 }
-// out = relu(a + b) on split tensors (block output for the folded-BN / no-norm encoders)
+// out = relu(a + b) on split tensors (block output for the folded-BN / no-norm encoders), 8 channels per thread
 __global__ void add_relu_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo, int a_stride,
                                 const __half* __restrict__ b_hi, const __half* __restrict__ b_lo, int b_stride,
                                 __half* __restrict__ o_hi, __half* __restrict__ o_lo, int o_stride, size_t npx, int C) {
+  const int c8 = C / 8;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npx * C) return;
-  const int c = i % C;
-  const size_t px = i / C;
-  const float y = fmaxf(join_f32(a_hi[px * a_stride + c], a_lo[px * a_stride + c]) +
-                            join_f32(b_hi[px * b_stride + c], b_lo[px * b_stride + c]), 0.f);
-  __half hi, lo;
-  split_f32(y, hi, lo);
-  o_hi[px * o_stride + c] = hi;
-  o_lo[px * o_stride + c] = lo;
+  if (i >= npx * c8) return;
+  const int c = (i % c8) * 8;
+  const size_t px = i / c8;
+  __align__(16) __half ah[8], al_[8], bh[8], bl[8], oh[8], ol[8];
+  *reinterpret_cast<uint4*>(ah) = *reinterpret_cast<const uint4*>(a_hi + px * a_stride + c);
+  *reinterpret_cast<uint4*>(al_) = *reinterpret_cast<const uint4*>(a_lo + px * a_stride + c);
+  *reinterpret_cast<uint4*>(bh) = *reinterpret_cast<const uint4*>(b_hi + px * b_stride + c);
+  *reinterpret_cast<uint4*>(bl) = *reinterpret_cast<const uint4*>(b_lo + px * b_stride + c);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) split_f32(fmaxf(join_f32(ah[k], al_[k]) + join_f32(bh[k], bl[k]), 0.f), oh[k], ol[k]);
+  *reinterpret_cast<uint4*>(o_hi + px * o_stride + c) = *reinterpret_cast<const uint4*>(oh);
+  *reinterpret_cast<uint4*>(o_lo + px * o_stride + c) = *reinterpret_cast<const uint4*>(ol);
 }
 
 // ---- workspace -----------------------------------------------------------------------------------------
@@ -263,10 +343,16 @@ static int enc_conv(const EncRun& R, int i, const float* img, SplitPtr in, int i
     same_pad(w, c.k, c.stride, &pl, &ow);
     size_t total = (size_t)R.B * oh * ow * pk.cin_pad;
     unsigned blocks = (unsigned)((total + 255) / 256);
-    if (img)
-      enc_gather_kernel<true><<<blocks, 256, 0, R.s>>>(img, nullptr, nullptr, 0, R.ws.col.hi, R.ws.col.lo, R.B, h, w, c.cin,
-                                                       c.k, c.stride, pt, pl, oh, ow, pk.cin_pad);
-    else
+    if (img) {
+      size_t t8 = total / 8;
+      enc_gather_img8_kernel<<<(unsigned)((t8 + 255) / 256), 256, 0, R.s>>>(img, R.ws.col.hi, R.ws.col.lo, R.B, h, w, c.cin, c.k,
+                                                                          c.stride, pt, pl, oh, ow, pk.cin_pad);
+    }
+    else if (c.cin % 8 == 0) {
+      size_t t8 = total / 8;
+      enc_gather8_kernel<<<(unsigned)((t8 + 255) / 256), 256, 0, R.s>>>(in.hi, in.lo, in_stride, R.ws.col.hi, R.ws.col.lo, R.B, h, w,
+                                                                      c.cin, c.k, c.stride, pt, pl, oh, ow, pk.cin_pad);
+    } else
       enc_gather_kernel<false><<<blocks, 256, 0, R.s>>>(nullptr, in.hi, in.lo, in_stride, R.ws.col.hi, R.ws.col.lo, R.B, h, w,
                                                         c.cin, c.k, c.stride, pt, pl, oh, ow, pk.cin_pad);
     RB_CHECK_LAUNCH("enc_gather_kernel");
@@ -296,9 +382,9 @@ static int enc_conv(const EncRun& R, int i, const float* img, SplitPtr in, int i
     dim3 g1(kStrips, R.B);
     inorm_partial_kernel<<<g1, rows * C, 2 * rows * C * sizeof(double), R.s>>>(R.ws.f32, R.ws.part, npx, C, kStrips);
     RB_CHECK_LAUNCH("inorm_partial_kernel");
-    inorm_final_kernel<<<R.B, 256, 0, R.s>>>(R.ws.part, R.ws.stat, npx, C, kStrips);
+    inorm_final_kernel<<<dim3(C, R.B), 256, 0, R.s>>>(R.ws.part, R.ws.stat, npx, C, kStrips);
     RB_CHECK_LAUNCH("inorm_final_kernel");
-    size_t n = (size_t)R.B * npx * C;
+    size_t n = (size_t)R.B * npx * (C / 8);
     inorm_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, R.s>>>(R.ws.f32, R.ws.stat, res.hi, res.lo, res_stride, dst.hi,
                                                                      dst.lo, dst_stride, R.B, npx, C, relu);
     RB_CHECK_LAUNCH("inorm_apply_kernel");
@@ -308,7 +394,7 @@ static int enc_conv(const EncRun& R, int i, const float* img, SplitPtr in, int i
     if ((rc = launch_conv(p, R.s))) return rc;
     if (res.hi) {
       size_t npx = (size_t)R.B * oh * ow;
-      size_t n = npx * pk.cout;
+      size_t n = npx * (pk.cout / 8);
       add_relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, R.s>>>(res.hi, res.lo, res_stride, dst.hi, dst.lo, dst_stride, dst.hi,
                                                                     dst.lo, dst_stride, npx, pk.cout);
       RB_CHECK_LAUNCH("add_relu_kernel");

@@ -286,8 +286,32 @@ static void set_act(ConvParams& p, int act, SplitPtr d0, int stride0, int choff0
   p.d0_hi = d0.hi; p.d0_lo = d0.lo; p.d0_stride = stride0; p.d0_choff = choff0;
 }
 
+// Second stream for the flow branch of the motion encoder (convf1 -> convf2), which is independent of the
+// correlation branch (lookup -> convc1 -> convc2) until encoder/conv joins them (model_utils.py:112-118).
+// At batch 1 a conv uses 55-110 of the 148 SMs, so the two branches genuinely overlap.  Fork/join with
+// events is also how the branch is expressed inside a CUDA-graph capture.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+static int side_stream(SideStream** out) {
+  static thread_local SideStream ss;
+  int dev = 0;
+  RB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (ss.device != dev) {
+    RB_CHECK_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+    RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    ss.device = dev;
+  }
+  *out = &ss;
+  return RB_OK;
+}
+
+// pyramid != nullptr: the lookup for this iteration is issued here too (on the main branch)
 static int update_step(const Variant& v, const void* blob, void* wsp, float* coords1, float* delta_out,
-                       float* mask_out, int B, int h, int w, cudaStream_t s) {
+                       float* mask_out, int B, int h, int w, cudaStream_t s, const float* pyramid = nullptr) {
   const size_t npix = (size_t)B * h * w;
   const PackedLayout L = packed_layout(v);
   const Workspace W = workspace_layout(v, npix, wsp);
@@ -296,14 +320,26 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   const int foff = xoff + v.mo_out;       // channel offset of the raw flow
   int rc;
   // ---- motion encoder (model_utils.py:110-129) ----
-  {
+  SideStream* ss;
+  if ((rc = side_stream(&ss))) return rc;
+  RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
+  RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
     dim3 grid((w + 31) / 32, h, B);
     const float* Wf = reinterpret_cast<const float*>(bb + L.f1_w);
     const float* bf = reinterpret_cast<const float*>(bb + L.f1_b);
     const float2* c1 = reinterpret_cast<const float2*>(coords1);
-    if (v.small) flow_conv7_kernel<64><<<grid, 64, 0, s>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
-    else flow_conv7_kernel<128><<<grid, 128, 0, s>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
+    if (v.small) flow_conv7_kernel<64><<<grid, 64, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
+    else flow_conv7_kernel<128><<<grid, 128, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
     RB_CHECK_LAUNCH("flow_conv7_kernel");
+    ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
+    set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
+    if ((rc = launch_conv(p, ss->stream))) return rc;
+    RB_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
+  }
+  // correlation branch (main stream): [lookup ->] convc1 [-> convc2]
+  if (pyramid) {
+    if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s))) return rc;
   }
   if (!v.small) {
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
@@ -317,11 +353,9 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
     if ((rc = launch_conv(p, s))) return rc;
   }
+  RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   {
-    ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
-    set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
-    if ((rc = launch_conv(p, s))) return rc;
-    p = base_params(v, L, blob, P_MOTION, W.cf, v.cf, 0, B, h, w);
+    ConvParams p = base_params(v, L, blob, P_MOTION, W.cf, v.cf, 0, B, h, w);
     set_act(p, ACT_RELU, W.hx, v.hx, xoff);
     p.d1_hi = W.qx.hi; p.d1_lo = W.qx.lo; p.d1_stride = v.hx; p.d1_choff = xoff;
     if ((rc = launch_conv(p, s))) return rc;
@@ -533,9 +567,8 @@ extern "C" int rb_raft_iterate(int small, const void* weights, void* workspace, 
   if (rc) return rc;
   const Variant& v = variant(small);
   for (int it = 0; it < iters; ++it) {
-    if ((rc = rb_update_lookup(small, workspace, pyramid, coords1, B, h, w, stream))) return rc;
     float* m = (it == iters - 1 && !small) ? mask_out : nullptr;
-    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream))) return rc;
+    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream, pyramid))) return rc;
   }
   return RB_OK;
 }
