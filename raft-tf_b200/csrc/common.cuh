@@ -102,7 +102,13 @@ struct ConvParams {
   float* f2;
 };
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate non-linearities on the SFU: exp via ex2.approx (abs. error of the gate < 3e-7 for |x| < 16, i.e.
+// below the 2^-22 operand truncation of the split GEMM that feeds them), reciprocal via rcp.approx.
+// r01 profile: with libm expf/tanhf + IEEE division the GRU epilogues took as long as their MMA loops.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) {  // 1 - 2/(1+e^{2x}); exact limits at +-inf
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+}
 
 // Store NV consecutive output channels [c, c+NV) of pixel `pix`; v holds acc (bias not yet added).
 // c is a multiple of NV; channel offsets of every destination are multiples of 8.
@@ -196,7 +202,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
       load_f32(p.f1 + (size_t)pix * p.hidden + c, hprev);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const float q = tanhf(y[i]);
+        const float q = tanh_f(y[i]);
         y[i] = (1.0f - z[i]) * hprev[i] + z[i] * q;  // model_utils.py:147,155,168
       }
       store_f32(p.f1 + (size_t)pix * p.hidden + c, y);

@@ -10,9 +10,11 @@
 //     D[:, N:2N]   += A_lo x  B_hi^T
 // so TMEM columns [0,N) hold hi*hi and [N,2N) hold the two cross terms (2^11-scaled); the
 // epilogue forms hi*hi + 2^-11 * cross in fp32 and applies the fused epilogue of common.cuh.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue: warp w reads TMEM lane
-// quarter (w % 4) and, when BLOCK_N >= 32, column half (w - 2) / 4 (profiles/r01: the epilogue, not
-// the MMA loop, was the longer phase with 4 warps).
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..17 = epilogue: warp w reads TMEM lane
+// quarter (w % 4) and column group (w - 2) / 4 of 16 or 32 columns (profiles/r01: with 4 and then 8
+// epilogue warps the dependent ALU chains of the epilogue took as long as the MMA loop).
+// Programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) runs
+// before griddepcontrol.wait, i.e. overlapped with the tail of the previous kernel in the stream.
 #include <unordered_map>
 #include <string.h>
 
@@ -24,7 +26,7 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled row
 constexpr int kATileBytes = kTileM * 128;  // 16 KB
-constexpr int kTcThreads = 320;            // 10 warps
+constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 
 // SHALLOW = 2 pipeline stages and two CTAs per SM: for convs with many pixel tiles and a short K loop
 // (the encoder layers) the epilogue of one CTA overlaps the MMA loop of its neighbour.  Otherwise
@@ -82,6 +84,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: let the next kernel in the stream start its own prologue, then wait until everything this kernel
+  // depends on (the previous kernels' outputs) is complete and visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -127,22 +133,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       umma_commit(tmem_full_bar);
     }
   } else {
-    // ---- epilogue: warps 2..9 ----
+    // ---- epilogue: warps 2..17 ----
     const int q = warp & 3;
-    constexpr int kHalves = BLOCK_N >= 32 ? 2 : 1;
-    constexpr int kColsPerWarp = BLOCK_N / kHalves;
-    const int half = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BLOCK_N >= 128 ? 32 : (BLOCK_N == 96 ? 32 : 16);
+    constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1
+    const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // tile row = pixel index inside the box
     const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
     const bool valid = (py < p.h) && (px < p.w);
     const int pix = (b * p.h + py) * p.w + px;
-    if (half < kHalves) {
+    if (grp < kGroups) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp; cc += 16) {
-        const int c = half * kColsPerWarp + cc;
+        const int c = grp * kColsPerWarp + cc;
         if (n0 + c >= p.cout) break;  // warp-uniform
         uint32_t d0[16], d1[16];
         tmem_ld16(trow + c, d0);
@@ -288,8 +294,18 @@ static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap*
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid(p.B * g.tiles_x * g.tiles_y, (p.cout + BLOCK_N - 1) / BLOCK_N);
-  conv_tc_kernel<BLOCK_N, SHALLOW><<<grid, kTcThreads, Cfg::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], p, g);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(p.B * g.tiles_x * g.tiles_y, (p.cout + BLOCK_N - 1) / BLOCK_N);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, SHALLOW>, maps[0], maps[1], maps[2], maps[3], p, g));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
