@@ -231,7 +231,7 @@ struct TmapKeyHash {
   }
 };
 
-static int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                        const uint32_t* box) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey k;
@@ -310,7 +310,14 @@ static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap*
   return RB_OK;
 }
 
+int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled);
+
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
+  if (p.kh * p.kw > 1) {  // multi-tap convs: halo-tile kernel (each input pixel is fetched once per tap ROW, not per tap)
+    bool handled = false;
+    int rc = launch_conv_halo(p, s, &handled);
+    if (rc || handled) return rc;
+  }
   RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   const TileGeom g = choose_geom(p.h, p.w);

@@ -137,4 +137,9 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box);
 
 }  // namespace tc
+
+// per-thread cache of encoded tensor maps (conv_tc.cu)
+int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box);
+
 }  // namespace rb
