@@ -104,13 +104,14 @@ int rb_update_weights_pack(int small, const float* const* W_host, const float* c
  * activation.  Must be zero-filled by the caller once before first use (cudaMemset). */
 int rb_update_workspace_bytes(int small, int B, int h, int w, size_t* bytes);
 /* net = tanh(cnet[..., :hidden]) and inp = relu(cnet[..., hidden:]) (RAFT.py:85-87) are supplied
- * already activated: net [B,h,w,hidden], inp [B,h,w,context]. */
-int rb_update_set_state(int small, void* workspace, const float* net, const float* inp, int B,
-                        int h, int w, void* stream);
+ * already activated: net [B,h,w,hidden], inp [B,h,w,context].  `weights` is the packed blob: the
+ * iteration-invariant contribution of `inp` to the GRU convolutions is computed here, once per pair. */
+int rb_update_set_state(int small, const void* weights, void* workspace, const float* net,
+                        const float* inp, int B, int h, int w, void* stream);
 /* Same from the raw context-encoder output cnet [B,h,w,hidden+context]: applies the split, tanh and relu of
  * RAFT.py:85-87 itself. */
-int rb_update_set_state_cnet(int small, void* workspace, const float* cnet, int B, int h, int w,
-                             void* stream);
+int rb_update_set_state_cnet(int small, const void* weights, void* workspace, const float* cnet,
+                             int B, int h, int w, void* stream);
 int rb_update_get_net(int small, const void* workspace, float* net, int B, int h, int w,
                       void* stream);
 /* Lookup written straight into the workspace in the layout the first conv consumes (fast path). */

@@ -79,7 +79,12 @@ struct ConvParams {
   const __half* in_hi;
   const __half* in_lo;
   int in_stride, in_choff;
-  int cin_pad;  // channels consumed per tap (multiple of 64)
+  int cin_pad;  // channels per tap in the packed weights (multiple of 64)
+  // K sub-range: only the 64-channel chunks i in [0, ck_count) are multiplied, chunk i -> channel chunk
+  // ck(i) = ck_begin + i + (i >= ck_skip_at ? ck_skip : 0).  ck_count == 0 means "all chunks".
+  // (The iteration-invariant `inp` slice of the GRU inputs is convolved once per pair and skipped afterwards.)
+  int ck_begin, ck_count, ck_skip_at, ck_skip;
+  const float* addend;  // optional fp32 [pixel][cout] added to the accumulator before bias/activation
   // packed weights [cout_pad][kh*kw][cin_pad] (K-major) as split planes + fp32 bias
   const __half* w_hi;
   const __half* w_lo;
@@ -119,6 +124,19 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
 #pragma unroll
   for (int i = 0; i < NV; ++i) y[i] = v[i] + ((p.bias && c + i < p.cout) ? __ldg(p.bias + c + i) : 0.f);
   const bool full = (c + NV <= p.cout);
+  if (p.addend) {
+    const float* ad = p.addend + (size_t)pix * p.cout + c;
+    if (full && NV % 4 == 0 && (p.cout & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(ad + i));
+        y[i] += t.x; y[i + 1] += t.y; y[i + 2] += t.z; y[i + 3] += t.w;
+      }
+    } else {
+      for (int i = 0; i < NV; ++i)
+        if (c + i < p.cout) y[i] += __ldg(ad + i);
+    }
+  }
 
   auto load_f32 = [&](const float* src, float* dst) {  // NV consecutive floats, 4*NV-byte aligned
     if constexpr (NV % 4 == 0) {
@@ -242,5 +260,9 @@ inline int launch_conv(const ConvParams& p, cudaStream_t s) {
 }
 
 inline int level_dim(int d, int level) { return d >> level; }
+__host__ __device__ inline int conv_chunks(const ConvParams& p) { return p.ck_count > 0 ? p.ck_count : p.cin_pad / 64; }
+__host__ __device__ inline int conv_chunk(const ConvParams& p, int i) {
+  return p.ck_count > 0 ? p.ck_begin + i + (i >= p.ck_skip_at ? p.ck_skip : 0) : i;
+}
 
 }  // namespace rb

@@ -72,7 +72,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int ts = trem / g.tiles_f, tf = trem - ts * g.tiles_f;
   const int f0 = tf << g.p_log2, s0 = ts * g.q;  // tile origin along F and S
   const int n0 = blockIdx.y * BLOCK_N;
-  const int chunks = p.cin_pad / 64;
+  const int chunks = conv_chunks(p);
   const int groups = chunks * g.kF;
 
   if (warp == 0 && lane == 0) {
@@ -100,7 +100,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const uint32_t phase = (grp / kAStages) & 1;
         mbar_wait(&a_empty[st], phase ^ 1);
         mbar_arrive_expect_tx(&a_full[st], a_bytes);
-        const int ck = grp / g.kF, f = grp - ck * g.kF;
+        const int f = grp % g.kF, ck = conv_chunk(p, grp / g.kF);
         uint8_t* dst = smemA + st * kAStageBytes;
         const int c0 = p.in_choff + ck * 64;
         // box origin: F coordinate shifted by the F-tap, S coordinate by -padS (halo covers all S-taps)
@@ -111,7 +111,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       int bi = 0;
       issue_a(0);
       for (int grp = 0; grp < groups; ++grp) {
-        const int ck = grp / g.kF, f = grp - ck * g.kF;
+        const int f = grp % g.kF, ck = conv_chunk(p, grp / g.kF);
         for (int s = 0; s < g.kS; ++s, ++bi) {
           const int st = bi % NB;
           const uint32_t phase = (bi / NB) & 1;
@@ -269,7 +269,7 @@ int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled) {
   const long m_tiles = (long)p.B * g.tiles_f * g.tiles_s;
   // many pixel tiles and a short K loop (encoder layers): the 2-CTA/SM shallow kernel of conv_tc.cu overlaps
   // epilogues with MMA loops, which matters more there than operand traffic
-  if (m_tiles > 2 * 148 && p.kh * p.kw * (p.cin_pad / 64) <= 18 && p.cout <= 64) return RB_OK;
+  if (m_tiles > 2 * 148 && p.kh * p.kw * conv_chunks(p) <= 18 && p.cout <= 64) return RB_OK;
   const int bn = halo_block_n(p.cout, m_tiles);
   CUtensorMap maps[4];
   {

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
     const size_t src = ((size_t)(lb * p.h + sy) * p.w + sx) * p.in_stride + p.in_choff;
     const size_t wrow = ((size_t)(co0 + lr) * taps + t) * p.cin_pad;
     const bool w_ok = (co0 + lr) < p.cout_pad;
-    for (int k0 = 0; k0 < p.cin_pad; k0 += 16) {
+    for (int kk = 0; kk < conv_chunks(p) * 64; kk += 16) {
+      const int k0 = conv_chunk(p, kk >> 6) * 64 + (kk & 63);
       float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
       if (in_img) {
         uint2 h = *reinterpret_cast<const uint2*>(p.in_hi + src + k0 + lk);

@@ -15,6 +15,7 @@
 // epilogue warps the dependent ALU chains of the epilogue took as long as the MMA loop).
 // Programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) runs
 // before griddepcontrol.wait, i.e. overlapped with the tail of the previous kernel in the stream.
+#include <stdlib.h>
 #include <unordered_map>
 #include <string.h>
 
@@ -50,9 +51,8 @@ template <int BLOCK_N, bool SHALLOW>
 __global__ void __launch_bounds__(kTcThreads, (TcCfg<BLOCK_N, SHALLOW>::kMinBlocks))
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const ConvParams p, const TileGeom g) {
+               const ConvParams p, const TileGeom g, const int STAGES) {
   using Cfg = TcCfg<BLOCK_N, SHALLOW>;
-  constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
@@ -68,7 +68,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
   const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2;
   const int n0 = blockIdx.y * BLOCK_N;
-  const int chunks = p.cin_pad / kChunkK;
+  const int chunks = conv_chunks(p);
   const int taps = p.kh * p.kw;
   const int kiters = taps * chunks;
 
@@ -99,7 +99,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&empty_bar[s], phase ^ 1);
         uint8_t* st = smem + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        const int t = it / chunks, ck = it - t * chunks;
+        const int t = it / chunks, ck = conv_chunk(p, it - t * chunks);
         const int dy = t / p.kw - ph, dx = t % p.kw - pw;
         const int c0 = p.in_choff + ck * kChunkK;
         tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
@@ -305,7 +305,10 @@ static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap*
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, SHALLOW>, maps[0], maps[1], maps[2], maps[3], p, g));
+  int stages = Cfg::kStages;
+  static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
+  if (env_stages > 0 && env_stages < stages) stages = env_stages;
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, SHALLOW>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
@@ -342,7 +345,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
     if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
   }
   const long ctas = m_tiles * ((p.cout + bn - 1) / bn);
-  const int kiters = p.kh * p.kw * (p.cin_pad / kChunkK);
+  const int kiters = p.kh * p.kw * conv_chunks(p);
   const bool shallow = bn <= 64 && ctas > 2 * 148 && kiters <= 18;
   switch (bn) {
     case 16: return shallow ? launch_cfg<16, true>(p, g, maps, s) : launch_cfg<16, false>(p, g, maps, s);

@@ -114,6 +114,7 @@ struct Workspace {
   SplitPtr corr, c1, cf, f1, hx, qx, fh;
   float* H;
   float* Z;
+  float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
   size_t total;
 };
 
@@ -139,6 +140,13 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
   size_t fsz = align_up(npix * (size_t)v.hidden * sizeof(float), 1024);
   W.H = reinterpret_cast<float*>(b + off); off += fsz;
   W.Z = reinterpret_cast<float*>(b + off); off += fsz;
+  for (int i = 0; i < 4; ++i) {
+    W.pre[i] = nullptr;
+    if (!v.small) {
+      W.pre[i] = reinterpret_cast<float*>(b + off);
+      off += align_up(npix * (size_t)((i & 1) ? v.hidden : 2 * v.hidden) * sizeof(float), 1024);
+    }
+  }
   W.total = off;
   return W;
 }
@@ -281,6 +289,20 @@ static ConvParams base_params(const Variant& v, const PackedLayout& L, const voi
   return p;
 }
 
+// The `inp` slice of the GRU inputs ([h|inp|motion|flow], model_utils.py:141,144,150,153) never changes during
+// the iterations of one pair (RAFT.py:85-87,97-101), so its contribution (and the bias) to the z|r and q
+// convolutions is computed once in rb_update_set_state* and added in the epilogue: the per-iteration K loop
+// skips those channels (-1/3 of the GRU MMA work and operand traffic; identical up to fp32 summation order).
+// Only when the slice is aligned to the 64-channel chunks (raft-things: [128,256)).
+static inline bool can_hoist(const Variant& v) { return !v.small && v.hidden % 64 == 0 && v.ctx % 64 == 0; }
+static void hoist_inp(const Variant& v, const Workspace& W, int idx, ConvParams& p) {
+  if (!can_hoist(v)) return;
+  const int total = v.hx / 64, inp0 = v.hidden / 64, ninp = v.ctx / 64;
+  p.ck_begin = 0; p.ck_count = total - ninp; p.ck_skip_at = inp0; p.ck_skip = ninp;
+  p.addend = W.pre[idx];
+  p.bias = nullptr;  // folded into the addend
+}
+
 static void set_act(ConvParams& p, int act, SplitPtr d0, int stride0, int choff0) {
   p.epi = EPI_ACT; p.act = act;
   p.d0_hi = d0.hi; p.d0_lo = d0.lo; p.d0_stride = stride0; p.d0_choff = choff0;
@@ -365,10 +387,12 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   for (int pass = 0; pass < passes; ++pass) {
     int zr = pass == 0 ? P_ZR1 : P_ZR2, q = pass == 0 ? P_Q1 : P_Q2;
     ConvParams p = base_params(v, L, blob, zr, W.hx, v.hx, 0, B, h, w);
+    hoist_inp(v, W, pass * 2 + 0, p);
     p.epi = EPI_ZR; p.f0 = W.Z; p.f1 = W.H;
     p.d0_hi = W.qx.hi; p.d0_lo = W.qx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
     if ((rc = launch_conv(p, s))) return rc;
     p = base_params(v, L, blob, q, W.qx, v.hx, 0, B, h, w);
+    hoist_inp(v, W, pass * 2 + 1, p);
     p.epi = EPI_Q; p.f0 = W.Z; p.f1 = W.H;
     p.d0_hi = W.hx.hi; p.d0_lo = W.hx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
     if ((rc = launch_conv(p, s))) return rc;
@@ -391,6 +415,23 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     p = base_params(v, L, blob, P_MASK2, W.fh, v.fh, 0, B, h, w);
     p.epi = EPI_F32; p.f0 = mask_out; p.scale = 0.25f;
     if ((rc = launch_conv(p, s))) return rc;
+  }
+  return RB_OK;
+}
+
+// conv over the `inp` channels only (+bias) of the four GRU convs -> W.pre[0..3] (fp32)
+static int precompute_inp(const Variant& v, const void* blob, void* wsp, int B, int h, int w, cudaStream_t s) {
+  if (!can_hoist(v)) return RB_OK;
+  const size_t npix = (size_t)B * h * w;
+  const PackedLayout L = packed_layout(v);
+  const Workspace W = workspace_layout(v, npix, wsp);
+  const int ids[4] = {P_ZR1, P_Q1, P_ZR2, P_Q2};
+  for (int i = 0; i < 4; ++i) {
+    ConvParams p = base_params(v, L, blob, ids[i], W.hx, v.hx, 0, B, h, w);  // inp lives in HX and QX alike
+    p.ck_begin = v.hidden / 64; p.ck_count = v.ctx / 64; p.ck_skip_at = 1 << 20; p.ck_skip = 0;
+    p.epi = EPI_F32; p.f0 = W.pre[i]; p.scale = 1.f;
+    int rc = launch_conv(p, s);
+    if (rc) return rc;
   }
   return RB_OK;
 }
@@ -483,9 +524,9 @@ extern "C" int rb_update_workspace_bytes(int small, int B, int h, int w, size_t*
   return RB_OK;
 }
 
-extern "C" int rb_update_set_state(int small, void* workspace, const float* net, const float* inp, int B, int h,
-                                   int w, void* stream) {
-  RB_REQUIRE(workspace && net && inp, RB_ERR_BAD_ARG, "rb_update_set_state: null pointer");
+extern "C" int rb_update_set_state(int small, const void* weights, void* workspace, const float* net, const float* inp,
+                                   int B, int h, int w, void* stream) {
+  RB_REQUIRE(weights && workspace && net && inp, RB_ERR_BAD_ARG, "rb_update_set_state: null pointer");
   int rc = check_shape("rb_update_set_state", B, h, w);
   if (rc) return rc;
   const Variant& v = variant(small);
@@ -495,11 +536,12 @@ extern "C" int rb_update_set_state(int small, void* workspace, const float* net,
   set_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(net, inp, W, (int)npix, v.hidden,
                                                                                   v.ctx, v.hx);
   RB_CHECK_LAUNCH("set_state_kernel");
-  return RB_OK;
+  return precompute_inp(v, weights, workspace, B, h, w, (cudaStream_t)stream);
 }
 
-extern "C" int rb_update_set_state_cnet(int small, void* workspace, const float* cnet, int B, int h, int w, void* stream) {
-  RB_REQUIRE(workspace && cnet, RB_ERR_BAD_ARG, "rb_update_set_state_cnet: null pointer");
+extern "C" int rb_update_set_state_cnet(int small, const void* weights, void* workspace, const float* cnet, int B, int h,
+                                        int w, void* stream) {
+  RB_REQUIRE(weights && workspace && cnet, RB_ERR_BAD_ARG, "rb_update_set_state_cnet: null pointer");
   int rc = check_shape("rb_update_set_state_cnet", B, h, w);
   if (rc) return rc;
   const Variant& v = variant(small);
@@ -508,7 +550,7 @@ extern "C" int rb_update_set_state_cnet(int small, void* workspace, const float*
   size_t n = npix * (v.hidden + v.ctx);
   set_state_cnet_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cnet, W, (int)npix, v.hidden, v.ctx, v.hx);
   RB_CHECK_LAUNCH("set_state_cnet_kernel");
-  return RB_OK;
+  return precompute_inp(v, weights, workspace, B, h, w, (cudaStream_t)stream);
 }
 
 extern "C" int rb_update_get_net(int small, const void* workspace, float* net, int B, int h, int w, void* stream) {

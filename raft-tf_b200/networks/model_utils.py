@@ -90,7 +90,7 @@ def _update_block(small, net, inp, corr, flow, with_mask):
         st = capi.stream()
         net, inp = net.contiguous().float(), inp.contiguous().float()
         corr, flow = corr.contiguous().float(), flow.contiguous().float()
-        capi.check(lib.rb_update_set_state(s, capi.ptr(ws), capi.ptr(net), capi.ptr(inp), B, h, w, st))
+        capi.check(lib.rb_update_set_state(s, capi.ptr(blob), capi.ptr(ws), capi.ptr(net), capi.ptr(inp), B, h, w, st))
         capi.check(lib.rb_update_set_corr(s, capi.ptr(ws), capi.ptr(corr), B, h, w, st))
         from .utils import coords_grid
         coords1 = (flow + coords_grid(B, h, w, dev)).contiguous()

@@ -41,8 +41,8 @@ SIGNATURES = {
     "rb_update_weights_bytes": (_i, [_i, _psz]),
     "rb_update_weights_pack": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _vp]),
     "rb_update_workspace_bytes": (_i, [_i, _i, _i, _i, _psz]),
-    "rb_update_set_state": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "rb_update_set_state_cnet": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
+    "rb_update_set_state": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rb_update_set_state_cnet": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_get_net": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_lookup": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_set_corr": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),

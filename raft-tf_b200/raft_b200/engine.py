@@ -91,7 +91,7 @@ class RaftEngine:
         capi.check(lib.rb_set_math_mode(self.math_mode))
         capi.check(lib.rb_corr_build(capi.ptr(self.fmap1), capi.ptr(self.fmap2), capi.ptr(self.pyramid), B, h, w,
                                      self.fdim, capi.ptr(self.corr_ws), self.cws_bytes, st))
-        capi.check(lib.rb_update_set_state_cnet(s, capi.ptr(self.ws), capi.ptr(self.cmap), B, h, w, st))
+        capi.check(lib.rb_update_set_state_cnet(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.cmap), B, h, w, st))
         capi.check(lib.rb_coords_grid(capi.ptr(self.coords1), B, h, w, st))
         capi.check(lib.rb_raft_iterate(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.pyramid),
                                        capi.ptr(self.coords1), capi.ptr(self.mask), B, h, w, self.iters, st))
