@@ -54,6 +54,10 @@ int rb_get_math_mode(void);
 long long rb_launch_count(void);
 void rb_launch_count_reset(void);
 
+/* Profiling aid: when buf != NULL, rb_update_step records 8 globaltimer timestamps per CTA of each of its
+ * tensor-core convs into buf (int64[n_convs][4096][8], launch order); NULL switches it off. */
+int rb_debug_set_buffer(void* buf);
+
 /* ---- A4: coords_grid(batch, ht, wd)  networks/utils.py:4-11 ----------------------------------
  * coords[b,y,x,0] = x, coords[b,y,x,1] = y. */
 int rb_coords_grid(float* coords, int B, int h, int w, void* stream);

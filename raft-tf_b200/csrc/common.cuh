@@ -85,6 +85,8 @@ struct ConvParams {
   // (The iteration-invariant `inp` slice of the GRU inputs is convolved once per pair and skipped afterwards.)
   int ck_begin, ck_count, ck_skip_at, ck_skip;
   const float* addend;  // optional fp32 [pixel][cout] added to the accumulator before bias/activation
+  int pdl_early;        // 1: trigger dependents at kernel start instead of at epilogue start (tuning knob)
+  long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py
   // packed weights [cout_pad][kh*kw][cin_pad] (K-major) as split planes + fp32 bias
   const __half* w_hi;
   const __half* w_lo;
@@ -259,6 +261,11 @@ inline int launch_conv(const ConvParams& p, cudaStream_t s) {
   return math_mode() == RB_MATH_SIMT ? launch_conv_simt(p, s) : launch_conv_tc(p, s);
 }
 
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 inline int level_dim(int d, int level) { return d >> level; }
 __host__ __device__ inline int conv_chunks(const ConvParams& p) { return p.ck_count > 0 ? p.ck_count : p.cin_pad / 64; }
 __host__ __device__ inline int conv_chunk(const ConvParams& p, int i) {

@@ -65,6 +65,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   const int P = 1 << g.p_log2;
   const int tiles_per_img = g.tiles_f * g.tiles_s;
   const int b = blockIdx.x / tiles_per_img;
@@ -88,8 +90,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
+  if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (dbg && threadIdx.x == 0) dbg[2] = gtime_ns();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -141,6 +145,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const int st = bi % NB;
           mbar_wait(&b_full[st], (bi / NB) & 1);
           tc_fence_after();
+          if (dbg && bi == 0) dbg[3] = gtime_ns();
           const uint32_t view = a_base + (uint32_t)(s * P) * 128u;  // shifted by s taps along S: multiple of 1024 B
           const uint64_t a_hi = umma_desc_sw128(view);
           const uint64_t a_lo = umma_desc_sw128(view + (uint32_t)g.halo_rows * 128u);
@@ -156,6 +161,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         umma_commit(&a_empty[ast]);
       }
       umma_commit(tmem_full_bar);
+      if (dbg) dbg[4] = gtime_ns();
     }
   } else {
     const int q = warp & 3;
@@ -170,6 +176,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (grp < kGroups) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      // PDL trigger: only now (MMA loop done, epilogue starting) may the next kernel's CTAs be scheduled -- triggering
+      // at kernel start let them take the SMs this kernel's own late CTAs were waiting for (phase_times.py).
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      if (dbg && warp == 2 && lane == 0) dbg[5] = gtime_ns();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp; cc += 16) {
@@ -189,8 +199,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
   }
+  if (dbg && warp == 2 && lane == 0) dbg[6] = gtime_ns();
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[7] = gtime_ns();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -61,6 +61,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   // tile coordinates
   const int tiles_per_img = g.tiles_x * g.tiles_y;
   const int b = blockIdx.x / tiles_per_img;
@@ -84,10 +86,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: let the next kernel in the stream start its own prologue, then wait until everything this kernel
-  // depends on (the previous kernels' outputs) is complete and visible.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // PDL: wait until everything this kernel depends on (the previous kernels' outputs) is complete and visible.
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
+  if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (dbg && threadIdx.x == 0) dbg[2] = gtime_ns();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -118,6 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t phase = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], phase);
         tc_fence_after();
+        if (dbg && it == 0) dbg[3] = gtime_ns();
         const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
         const uint64_t a_hi = umma_desc_sw128(st);
         const uint64_t a_lo = umma_desc_sw128(st + kATileBytes);
@@ -131,6 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
       }
       umma_commit(tmem_full_bar);
+      if (dbg) dbg[4] = gtime_ns();
     }
   } else {
     // ---- epilogue: warps 2..17 ----
@@ -145,6 +150,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (grp < kGroups) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      // PDL trigger: only now (MMA loop done, epilogue starting) may the next kernel's CTAs be scheduled -- triggering
+      // at kernel start let them take the SMs this kernel's own late CTAs were waiting for (phase_times.py).
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      if (dbg && warp == 2 && lane == 0) dbg[5] = gtime_ns();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < kColsPerWarp; cc += 16) {
@@ -164,8 +173,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   }
+  if (dbg && warp == 2 && lane == 0) dbg[6] = gtime_ns();
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[7] = gtime_ns();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -12,6 +12,7 @@
 //   FH   [fh]     relu(flow_head/conv1); reused for relu(mask/0)
 //   H, Z fp32 [hidden]  recurrent state and the update gate
 // Concatenations are never materialised: producers write at channel offsets of HX/QX/CF.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -294,13 +295,27 @@ static ConvParams base_params(const Variant& v, const PackedLayout& L, const voi
 // convolutions is computed once in rb_update_set_state* and added in the epilogue: the per-iteration K loop
 // skips those channels (-1/3 of the GRU MMA work and operand traffic; identical up to fp32 summation order).
 // Only when the slice is aligned to the 64-channel chunks (raft-things: [128,256)).
-static inline bool can_hoist(const Variant& v) { return !v.small && v.hidden % 64 == 0 && v.ctx % 64 == 0; }
+static inline bool can_hoist(const Variant& v) {
+  static const bool off = getenv("RAFT_B200_NO_HOIST") != nullptr;  // A/B knob
+  return !off && !v.small && v.hidden % 64 == 0 && v.ctx % 64 == 0;
+}
 static void hoist_inp(const Variant& v, const Workspace& W, int idx, ConvParams& p) {
   if (!can_hoist(v)) return;
   const int total = v.hx / 64, inp0 = v.hidden / 64, ninp = v.ctx / 64;
   p.ck_begin = 0; p.ck_count = total - ninp; p.ck_skip_at = inp0; p.ck_skip = ninp;
   p.addend = W.pre[idx];
   p.bias = nullptr;  // folded into the addend
+}
+
+// Phase-timestamp debug buffer (tools/phase_times.py): rb_debug_set_buffer(ptr, convs) makes the next update
+// step record 8 timestamps per CTA for each of its convs, in launch order, 4096 CTAs per conv.
+static thread_local long long* g_dbg = nullptr;
+static thread_local int g_dbg_idx = 0;
+static int launch_conv_dbg(ConvParams& p, cudaStream_t s) {
+  static const int early = getenv("RAFT_B200_PDL_EARLY") ? 1 : 0;
+  p.pdl_early = early;
+  if (g_dbg) p.dbg = g_dbg + (size_t)(g_dbg_idx++) * 4096 * 8;
+  return launch_conv(p, s);
 }
 
 static void set_act(ConvParams& p, int act, SplitPtr d0, int stride0, int choff0) {
@@ -341,6 +356,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   const int xoff = v.hidden + v.ctx;      // channel offset of motion_out inside HX/QX
   const int foff = xoff + v.mo_out;       // channel offset of the raw flow
   int rc;
+  g_dbg_idx = 0;
   // ---- motion encoder (model_utils.py:110-129) ----
   SideStream* ss;
   if ((rc = side_stream(&ss))) return rc;
@@ -356,7 +372,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     RB_CHECK_LAUNCH("flow_conv7_kernel");
     ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
-    if ((rc = launch_conv(p, ss->stream))) return rc;
+    if ((rc = launch_conv_dbg(p, ss->stream))) return rc;
     RB_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
   }
   // correlation branch (main stream): [lookup ->] convc1 [-> convc2]
@@ -366,21 +382,21 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   if (!v.small) {
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
     set_act(p, ACT_RELU, W.c1, v.c1, 0);
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
     p = base_params(v, L, blob, P_CONVC2, W.c1, v.c1, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
   } else {
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   {
     ConvParams p = base_params(v, L, blob, P_MOTION, W.cf, v.cf, 0, B, h, w);
     set_act(p, ACT_RELU, W.hx, v.hx, xoff);
     p.d1_hi = W.qx.hi; p.d1_lo = W.qx.lo; p.d1_stride = v.hx; p.d1_choff = xoff;
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   // ---- GRU (model_utils.py:138-169) ----
   const int passes = v.small ? 1 : 2;
@@ -390,31 +406,31 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     hoist_inp(v, W, pass * 2 + 0, p);
     p.epi = EPI_ZR; p.f0 = W.Z; p.f1 = W.H;
     p.d0_hi = W.qx.hi; p.d0_lo = W.qx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
     p = base_params(v, L, blob, q, W.qx, v.hx, 0, B, h, w);
     hoist_inp(v, W, pass * 2 + 1, p);
     p.epi = EPI_Q; p.f0 = W.Z; p.f1 = W.H;
     p.d0_hi = W.hx.hi; p.d0_lo = W.hx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   // ---- flow head (model_utils.py:131-135) + coords1 += delta (RAFT.py:102) ----
   {
     ConvParams p = base_params(v, L, blob, P_FH1, W.hx, v.hx, 0, B, h, w);
     set_act(p, ACT_RELU, W.fh, v.fh, 0);
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
     p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
     p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   // ---- mask head (model_utils.py:180-183); only the last iteration's mask is ever consumed ----
   if (mask_out) {
     RB_REQUIRE(!v.small, RB_ERR_UNSUPPORTED, "raft-small has no mask head (model_utils.py:194)");
     ConvParams p = base_params(v, L, blob, P_MASK0, W.hx, v.hx, 0, B, h, w);
     set_act(p, ACT_RELU, W.fh, v.fh, 0);
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
     p = base_params(v, L, blob, P_MASK2, W.fh, v.fh, 0, B, h, w);
     p.epi = EPI_F32; p.f0 = mask_out; p.scale = 0.25f;
-    if ((rc = launch_conv(p, s))) return rc;
+    if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   return RB_OK;
 }
@@ -443,6 +459,11 @@ using namespace rb;
 static int check_shape(const char* fn, int B, int h, int w) {
   RB_REQUIRE(B > 0 && h > 0 && w > 0 && (size_t)B * h * w < (1u << 30), RB_ERR_BAD_SHAPE, "%s: bad shape B=%d h=%d w=%d",
              fn, B, h, w);
+  return RB_OK;
+}
+
+extern "C" int rb_debug_set_buffer(void* buf) {
+  g_dbg = reinterpret_cast<long long*>(buf);
   return RB_OK;
 }
 

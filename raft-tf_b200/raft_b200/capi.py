@@ -26,6 +26,7 @@ SIGNATURES = {
     "rb_get_math_mode": (_i, []),
     "rb_launch_count": (C.c_longlong, []),
     "rb_launch_count_reset": (None, []),
+    "rb_debug_set_buffer": (_i, [_vp]),
     "rb_coords_grid": (_i, [_vp, _i, _i, _i, _vp]),
     "rb_corr_pyramid_bytes": (_i, [_i, _i, _i, _psz]),
     "rb_corr_level_offset": (_i, [_i, _i, _i, _i, _psz, _pi, _pi]),
