@@ -281,13 +281,14 @@ def main():
     t_look_warm = ev_time(look, flush_l2=False)
     upd_flops = 2.0 * npix * UPDATE_MAC_PER_PX
     look_bytes = float(npix * LOOKUP_BYTES_PER_PX)
-    roof = {"kernel": "rb_update_step (11 conv_tc_kernel launches + flow_conv7)", "bound": "tensor",
+    roof = {"kernel": "rb_update_step: 10 tcgen05 convs (conv_halo_kernel / conv_tc_kernel) + flow_conv7_kernel", "bound": "tensor",
             "achieved": upd_flops / t_upd / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
             "frac": upd_flops / t_upd / 1e12 / pk["tf"], "traffic": None, "peak_source": pk["src"],
             "note": "algorithmic fp32-equivalent FLOPs; each product costs 3 fp16 MMAs (hi/lo split), so frac <= 1/3 by design",
             "us_per_launch_group": t_upd * 1e6}
     roof_l = {"kernel": "corr_lookup_kernel<4,split>", "bound": "hbm", "achieved": look_bytes / t_look / 1e9,
-              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": None,
+              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": 35.63e6 * B,
+              "traffic_note": "ncu --set full (profiles/r01_lookup_ncu_full.txt): dram read 35.6 MB + write 0.05 MB per cold launch",
               "peak_source": pk["src"], "us_per_launch": t_look * 1e6,
               "l2_warm": {"us_per_launch": t_look_warm * 1e6, "achieved": look_bytes / t_look_warm / 1e9,
                           "note": "same launch without the L2 flush: at B=1 the ~25 MB of patches around the current flow stay L2-resident between iterations"}}
