@@ -102,8 +102,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&empty_bar[s], phase ^ 1);
         uint8_t* st = smem + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        const int t = it / chunks, ck = conv_chunk(p, it - t * chunks);
-        const int dy = t / p.kw - ph, dx = t % p.kw - pw;
+        // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
+        // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
+        // per-sample runs bit for bit.
+        const int cki = it / taps, tt = it - cki * taps;
+        const int ck = conv_chunk(p, cki);
+        const int kx = tt / p.kh, ky = tt - kx * p.kh;
+        const int t = ky * p.kw + kx;
+        const int dy = ky - ph, dx = kx - pw;
         const int c0 = p.in_choff + ck * kChunkK;
         tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
         tma_load_4d(&tmA_lo, &full_bar[s], st + kATileBytes, c0, x0 + dx, y0 + dy, b);
