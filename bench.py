@@ -293,6 +293,21 @@ def main():
               "l2_warm": {"us_per_launch": t_look_warm * 1e6, "achieved": look_bytes / t_look_warm / 1e9,
                           "note": "same launch without the L2 flush: at B=1 the ~25 MB of patches around the current flow stay L2-resident between iterations"}}
 
+    # the same kernel on a batch whose touched footprint exceeds L2 (8 samples, random pyramid): the HBM-bound regime
+    try:
+        B8 = 8
+        pyr8 = torch.randn(capi.size_query(lib.rb_corr_pyramid_bytes, B8, h, w) // 4, device=dev)
+        ws8 = torch.zeros(capi.size_query(lib.rb_update_workspace_bytes, s, B8, h, w), dtype=torch.uint8, device=dev)
+        g8 = torch.stack(torch.meshgrid(torch.arange(w, device=dev), torch.arange(h, device=dev), indexing="xy"), -1).float()
+        c8 = (g8[None] + torch.rand(B8, h, w, 2, device=dev) * 16 - 8).contiguous()
+        t8 = ev_time(lambda: capi.check(lib.rb_update_lookup(s, capi.ptr(ws8), capi.ptr(pyr8), capi.ptr(c8), B8, h, w, capi.stream())))
+        roof_l["batch8"] = {"us_per_launch": t8 * 1e6, "achieved": B8 * h * w * LOOKUP_BYTES_PER_PX / t8 / 1e9,
+                            "frac": B8 * h * w * LOOKUP_BYTES_PER_PX / t8 / 1e9 / pk["hbm"],
+                            "note": "B=8 x 440x1024 grid, N(0,1) pyramid (2.1 GB), coords = grid + U(-8,8), L2 flushed"}
+        del pyr8, ws8
+    except Exception as e:  # noqa: BLE001 -- an extra, never fail the bench line for it
+        roof_l["batch8"] = {"error": str(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(effective_cores(), 32)

@@ -209,8 +209,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int kind) {
   EncodeTiledFn fn = encode_fn();
   RB_REQUIRE(fn, RB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5];
@@ -218,9 +218,10 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = kind == TMAP_F32_SW64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = kind == TMAP_F32_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RB_REQUIRE(r == CUDA_SUCCESS, RB_ERR_CUDA,
              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
@@ -234,6 +235,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // (and CUDA-graph capture, which bakes kernel parameters) pay nothing for the encode.
 struct TmapKey {
   const void* base;
+  uint64_t kind;
   uint64_t d[4];
   uint64_t s[4];
   uint32_t b[4];
@@ -249,15 +251,16 @@ struct TmapKeyHash {
 };
 
 int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                       const uint32_t* box) {
+                const uint32_t* box, int kind) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey k;
   memset(&k, 0, sizeof(k));
   k.base = base;
+  k.kind = (uint64_t)kind;
   for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.s[i] = (i + 1 < rank) ? strides[i] : 0; k.b[i] = box[i]; }
   auto it = cache.find(k);
   if (it != cache.end()) { *out = it->second; return RB_OK; }
-  int rc = make_tmap_f16(out, base, rank, dims, strides, box);
+  int rc = make_tmap(out, base, rank, dims, strides, box, kind);
   if (rc) return rc;
   if (cache.size() > 4096) cache.clear();
   cache.emplace(k, *out);

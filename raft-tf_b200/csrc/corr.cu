@@ -1,6 +1,8 @@
 // A1 (correlation volume + pyramid), A2/A3 (pyramid lookup), A4 (coords grid).
 // Reference: networks/model_utils.py:199-249, networks/utils.py:4-103.
-#include "common.cuh"
+#include <string.h>
+
+#include "tc_common.cuh"
 
 namespace rb {
 
@@ -83,44 +85,77 @@ __global__ void avgpool2_kernel(const float* __restrict__ src, float* __restrict
 // A2/A3  pyramid lookup (model_utils.py:224-249 + utils.py:39-103).
 //
 // A block handles PB = 8 query pixels x 4 levels = 32 "units"; thread = (unit, window row j).
-//   phase 1  the block stages, per unit, the (2r+3) rows x 16 columns of the level that cover every
-//            tap footprint ((2r+1)^2 taps share one fractional offset, +1 row/col of slack for the
-//            fp32 rounding of cx+dx): 16-byte loads from a 4-float-aligned column, row index clamped.
-//   phase 2  thread j of a unit computes the x-side of window column i=j (clamped x0/x1 relative to
-//            the staged columns, qx = x1c - x and 1 - qx) into a small shared table, and keeps the
-//            y-side of its own row j in registers: the separable index math is done once per row /
-//            column instead of once per tap.
-//   phase 3  each thread walks the (2r+1) taps of its row with the reference's exact arithmetic
-//            (trunc toward zero, clamp, weights from the CLAMPED x1/y1, add_n order; __fmul_rn /
-//            __fadd_rn forbid FMA contraction => bit-identical to the fp32 CPU oracle) and stores
-//            channel lvl*K + i*(2r+1) + j: the threads of a unit write consecutive addresses.
-// Output: fp32 [pix][4K] (rb_corr_lookup) or hi/lo fp16 planes with a padded channel stride (the
-// layout convc1 consumes).  r01 profile of the previous one-warp-per-unit kernel: 391 warp
-// instructions per unit, issue-bound (70 % issue slots, 22 % DRAM); this formulation needs ~110.
+//   phase 0  thread u computes the origin of unit u's footprint and -- when the level's rows are 16-byte
+//            aligned -- issues ONE TMA box load (16 columns x (2r+3) rows of fp32, 64-byte swizzle) for it:
+//            the (2r+1)^2 taps share one fractional offset, so their bilinear footprints tile a (2r+2)^2 patch
+//            (+1 row/col of slack for the fp32 rounding of cx+dx, +<=3 columns of alignment).  Out-of-image parts
+//            of the box are zero-filled and never indexed (tap indices are clamped like the reference's).
+//            Levels whose width is not a multiple of 4 are staged with plain loads instead.
+//   phase 1  thread j of a unit computes the x-side of window column i=j (clamped x0/x1 relative to the staged
+//            columns, qx = x1c - x and 1 - qx) into a shared table and keeps the y-side of its own row j in
+//            registers: the separable index math is done once per row / column instead of once per tap.
+//   phase 2  each thread walks the (2r+1) taps of its row with the reference's exact arithmetic (trunc toward
+//            zero, clamp, weights from the CLAMPED x1/y1, add_n order; __fmul_rn/__fadd_rn forbid FMA
+//            contraction => bit-identical to the fp32 CPU oracle).
+//   phase 3  split mode: results were collected in shared memory as [pixel][plane][channel]; the block writes
+//            them out as 16-byte rows (the r01 profile of the direct 2-byte stores: 31 store sectors per unit
+//            for 324 useful bytes).  fp32 mode (rb_corr_lookup) stores directly.
+// r01 history: v1 one warp per unit, 391 warp instructions per unit, issue-bound; v2 block-cooperative with LDG
+// staging, LSU-wavefront-bound (108 wavefronts per unit); v3 = this.
 // ---------------------------------------------------------------------------------------------
 struct PyramidView {
   const float* base[RB_NUM_LEVELS];
   int hl[RB_NUM_LEVELS], wl[RB_NUM_LEVELS];
-  int vec_ok[RB_NUM_LEVELS];  // level rows are 16-byte aligned (W % 4 == 0 and aligned base)
+  int tma_ok[RB_NUM_LEVELS];  // level rows are 16-byte aligned (W % 4 == 0, aligned base): TMA-stageable
+};
+struct PyramidMaps {
+  CUtensorMap m[RB_NUM_LEVELS];  // (W_l, H_l, B*N) fp32, box (16, 2r+3, 1), 64-byte swizzle
 };
 
-constexpr int kLookupPB = 8;    // pixels per block
-constexpr int kPatchCols = 16;  // staged columns per row
-constexpr int kPatchPitch = 20; // floats per staged row (16 + 4 padding: conflict-light column reads)
+constexpr int kLookupPB = 8;     // pixels per block
+constexpr int kPatchCols = 16;   // staged columns per row (64 bytes)
+constexpr int kUnitBytes = 1024; // shared bytes reserved per unit (>= (2r+3)*64, keeps the swizzle phase at 0)
+
+// float index of element (row, col) inside a unit's staged patch (CU_TENSOR_MAP_SWIZZLE_64B: the 16-byte chunk
+// index is XORed with bits [1,3) of the 64-byte row index)
+__device__ __forceinline__ int patch_idx(int row, int col) {
+  return row * kPatchCols + ((((col >> 2) ^ (row >> 1)) & 3) << 2) + (col & 3);
+}
 
 template <int R, bool SPLIT>
 __global__ void __launch_bounds__(kLookupPB * 4 * (2 * R + 1))
-corr_lookup_kernel(const __grid_constant__ PyramidView pv, const float2* __restrict__ coords,
-                   float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                   int out_stride, int npix) {
+corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMaps maps,
+                   const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
+                   __half* __restrict__ out_lo, int out_stride, int npix) {
   constexpr int D = 2 * R + 1, K = D * D, P = D + 2, UNITS = kLookupPB * 4, NT = UNITS * D;
-  __shared__ __align__(16) float patch[UNITS][P][kPatchPitch];
-  __shared__ __align__(16) float4 xtab[UNITS][D];
+  constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel and plane (324 -> 328, 196 -> 200)
+  extern __shared__ __align__(1024) uint8_t lk_smem[];
+  float* patch = reinterpret_cast<float*>(lk_smem);                                    // [UNITS][256 floats]
+  float4* xtab = reinterpret_cast<float4*>(lk_smem + UNITS * kUnitBytes);             // [UNITS][D]
+  __half* ostage = reinterpret_cast<__half*>(lk_smem + UNITS * kUnitBytes + UNITS * D * 16);  // [PB][2][OUTP]
   __shared__ int ubase[UNITS][2];  // bx4, by per unit
+  __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
   const int pix0 = blockIdx.x * kLookupPB;
 
-  // ---- phase 0: per-unit origin -------------------------------------------------------------
+  if (tid == 0 && (tc::smem_u32(lk_smem) & 1023u)) __trap();  // the swizzle phase assumes 1024-byte aligned unit slots
+  int n_tma = 0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) n_tma += pv.tma_ok[l] ? kLookupPB : 0;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async();
+    if (n_tma) tc::mbar_arrive_expect_tx(&bar, (uint32_t)(n_tma * P * kPatchCols * 4));
+  }
+  if (SPLIT) {  // channel padding of the staged output rows (never produced by a tap)
+    for (int e = tid; e < kLookupPB * 2 * (OUTP - 4 * K); e += NT) {
+      const int row = e / (OUTP - 4 * K), c = 4 * K + e % (OUTP - 4 * K);
+      ostage[row * OUTP + c] = __float2half_rn(0.f);
+    }
+  }
+  __syncthreads();
+  // ---- phase 0: per-unit origin, TMA issue --------------------------------------------------------------
   if (tid < UNITS) {
     const int u = tid, pl = u >> 2, lvl = u & 3;
     const int pix = min(pix0 + pl, npix - 1);
@@ -128,30 +163,30 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const float2* __restr
     const float inv = 1.0f / (float)(1 << lvl);  // centroid / 2**i (model_utils.py:239), exact
     const int H = pv.hl[lvl], W = pv.wl[lvl];
     const float xf0 = __fadd_rn(c.x * inv, (float)(-R)), yf0 = __fadd_rn(c.y * inv, (float)(-R));
-    const int bx = min(max((int)xf0, 0), W - 1);
-    ubase[u][0] = bx & ~3;
-    ubase[u][1] = min(max((int)yf0, 0), H - 1);
+    const int bx4 = min(max((int)xf0, 0), W - 1) & ~3;
+    const int by = min(max((int)yf0, 0), H - 1);
+    ubase[u][0] = bx4;
+    ubase[u][1] = by;
+    if (pv.tma_ok[lvl]) tc::tma_load_3d(&maps.m[lvl], &bar, lk_smem + u * kUnitBytes, bx4, by, pix);
   }
   __syncthreads();
-  // ---- phase 1: stage patches (UNITS * P rows * 4 chunks of 4 floats) -------------------------
-  for (int e = tid; e < UNITS * P * 4; e += NT) {
-    const int u = e / (P * 4), rem = e - u * (P * 4), py = rem >> 2, ch = rem & 3;
-    const int pl = u >> 2, lvl = u & 3;
-    const int pix = min(pix0 + pl, npix - 1);
-    const int H = pv.hl[lvl], W = pv.wl[lvl];
-    const int yy = min(ubase[u][1] + py, H - 1);
-    const int col = ubase[u][0] + ch * 4;
-    const float* row = pv.base[lvl] + ((size_t)pix * H + yy) * W;
-    float4 v;
-    if (pv.vec_ok[lvl]) {
-      v = __ldg(reinterpret_cast<const float4*>(row + col));  // may run past the row end: never indexed
-    } else {
+  // ---- fallback staging for levels TMA cannot address (W % 4 != 0) -------------------------------------------
+  if (n_tma < UNITS) {
+    for (int e = tid; e < UNITS * P * 4; e += NT) {  // one 4-column chunk per thread and round
+      const int u = e / (P * 4), rem = e - u * (P * 4), py = rem >> 2, ch = rem & 3;
+      const int lvl = u & 3;
+      if (pv.tma_ok[lvl]) continue;
+      const int pix = min(pix0 + (u >> 2), npix - 1);
+      const int H = pv.hl[lvl], W = pv.wl[lvl];
+      const int yy = min(ubase[u][1] + py, H - 1), col = ubase[u][0] + ch * 4;
+      const float* row = pv.base[lvl] + ((size_t)pix * H + yy) * W;
+      float4 v;
       v.x = __ldg(row + min(col + 0, W - 1)); v.y = __ldg(row + min(col + 1, W - 1));
       v.z = __ldg(row + min(col + 2, W - 1)); v.w = __ldg(row + min(col + 3, W - 1));
+      *reinterpret_cast<float4*>(&patch[u * (kUnitBytes / 4) + patch_idx(py, ch * 4)]) = v;  // a chunk stays contiguous
     }
-    *reinterpret_cast<float4*>(&patch[u][py][ch * 4]) = v;
   }
-  // ---- phase 2: separable index math ------------------------------------------------------------
+  // ---- phase 1: separable index math ---------------------------------------------------------------------------
   const int u = tid / D, j = tid - u * D;
   const int pl = u >> 2, lvl = u & 3;
   const int pix = pix0 + pl;
@@ -169,7 +204,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const float2* __restr
     const float qx = __fsub_rn((float)x1, x);  // utils.py:84 (clamped x1)
     const int bx4 = ubase[u][0];
     const int ax0 = min(max(x0 - bx4, 0), kPatchCols - 1), ax1 = min(max(x1 - bx4, 0), kPatchCols - 1);
-    xtab[u][j] = make_float4(qx, __fsub_rn(1.0f, qx), __int_as_float(ax0), __int_as_float(ax1));
+    xtab[u * D + j] = make_float4(qx, __fsub_rn(1.0f, qx), __int_as_float(ax0), __int_as_float(ax1));
   }
   const float y = __fadd_rn(cy, (float)(j - R));
   int y0 = (int)y;
@@ -178,28 +213,44 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const float2* __restr
   y1 = min(max(y1, 0), H - 1);
   const float qy = __fsub_rn((float)y1, y), pyw = __fsub_rn(1.0f, qy);  // utils.py:85
   const int by = ubase[u][1];
-  const float* row0 = &patch[u][min(max(y0 - by, 0), P - 1)][0];
-  const float* row1 = &patch[u][min(max(y1 - by, 0), P - 1)][0];
-  __syncthreads();
-  if (pix >= npix) return;
-  // ---- phase 3: taps of window row j ----------------------------------------------------------------
-  const size_t obase = (size_t)pix * out_stride + lvl * K + j;
+  const int r0 = min(max(y0 - by, 0), P - 1), r1 = min(max(y1 - by, 0), P - 1);
+  const float* pu = patch + u * (kUnitBytes / 4);
+  const int r0b = r0 * kPatchCols, r0x = (r0 >> 1) & 3, r1b = r1 * kPatchCols, r1x = (r1 >> 1) & 3;
+  __syncthreads();                       // xtab + fallback patches visible
+  if (n_tma) tc::mbar_wait(&bar, 0);     // TMA patches landed
+  // ---- phase 2: taps of window row j ------------------------------------------------------------------------------
+  const bool live = pix < npix;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    const float4 xt = xtab[u][i];
+    const float4 xt = xtab[u * D + i];
     const int ax0 = __float_as_int(xt.z), ax1 = __float_as_int(xt.w);
+    const int c0h = ax0 >> 2, c0l = ax0 & 3, c1h = ax1 >> 2, c1l = ax1 & 3;
     const float wa = __fmul_rn(xt.x, qy), wb = __fmul_rn(xt.x, pyw);  // utils.py:86-89
     const float wc = __fmul_rn(xt.y, qy), wd = __fmul_rn(xt.y, pyw);
-    const float Ia = row0[ax0], Ib = row1[ax0], Ic = row0[ax1], Id = row1[ax1];
+    const float Ia = pu[r0b + (((c0h ^ r0x) & 3) << 2) + c0l], Ib = pu[r1b + (((c0h ^ r1x) & 3) << 2) + c0l];
+    const float Ic = pu[r0b + (((c1h ^ r0x) & 3) << 2) + c1l], Id = pu[r1b + (((c1h ^ r1x) & 3) << 2) + c1l];
     const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
                               __fmul_rn(wd, Id));  // tf.add_n order (utils.py:98)
+    const int ch = lvl * K + i * D + j;
     if constexpr (SPLIT) {
       __half hi, lo;
       split_f32(v, hi, lo);
-      out_hi[obase + i * D] = hi;
-      out_lo[obase + i * D] = lo;
+      ostage[(pl * 2 + 0) * OUTP + ch] = hi;
+      ostage[(pl * 2 + 1) * OUTP + ch] = lo;
     } else {
-      out_f32[obase + i * D] = v;
+      if (live) out_f32[(size_t)pix * out_stride + ch] = v;
+    }
+  }
+  // ---- phase 3: coalesced 16-byte stores of the staged rows ----------------------------------------------------------
+  if constexpr (SPLIT) {
+    __syncthreads();
+    constexpr int V = OUTP / 8;  // uint4 per pixel-plane
+    for (int e = tid; e < kLookupPB * 2 * V; e += NT) {
+      const int row = e / V, v8 = e - row * V, p2 = row >> 1, plane = row & 1;
+      if (pix0 + p2 >= npix) continue;
+      const uint4 val = *reinterpret_cast<const uint4*>(ostage + row * OUTP + v8 * 8);
+      __half* dst = (plane ? out_lo : out_hi) + (size_t)(pix0 + p2) * out_stride + v8 * 8;
+      *reinterpret_cast<uint4*>(dst) = val;
     }
   }
 }
@@ -237,9 +288,30 @@ int pyramid_view(const float* pyramid, int B, int h, int w, PyramidView* pv) {
     pv->base[l] = pyramid + off;
     pv->hl[l] = hl;
     pv->wl[l] = wl;
-    pv->vec_ok[l] = (wl % 4 == 0) && (reinterpret_cast<uintptr_t>(pyramid + off) % 16 == 0);
+    pv->tma_ok[l] = (wl % 4 == 0) && (reinterpret_cast<uintptr_t>(pyramid + off) % 16 == 0);
     off += rows * hl * wl;
   }
+  return RB_OK;
+}
+
+template <int R>
+static size_t lookup_smem_bytes() {
+  constexpr int D = 2 * R + 1, K = D * D, OUTP = (4 * K + 7) / 8 * 8, UNITS = kLookupPB * 4;
+  return (size_t)UNITS * kUnitBytes + (size_t)UNITS * D * 16 + (size_t)kLookupPB * 2 * OUTP * 2;
+}
+
+template <int R, bool SPLIT>
+static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, const float2* c2, float* out_f32, __half* out_hi,
+                             __half* out_lo, int out_stride, int npix, cudaStream_t s) {
+  static bool attr_set = false;
+  const size_t smem = lookup_smem_bytes<R>();
+  if (!attr_set) {
+    RB_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<R, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((npix + kLookupPB - 1) / kLookupPB), block(kLookupPB * 4 * (2 * R + 1));
+  corr_lookup_kernel<R, SPLIT><<<grid, block, smem, s>>>(pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix);
+  RB_CHECK_LAUNCH("corr_lookup_kernel");
   return RB_OK;
 }
 
@@ -248,24 +320,26 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
   PyramidView pv;
   int rc = pyramid_view(pyramid, B, h, w, &pv);
   if (rc) return rc;
-  int npix = B * h * w;
-  dim3 grid((npix + kLookupPB - 1) / kLookupPB);
-  const float2* c2 = reinterpret_cast<const float2*>(coords);
-  bool split = out_hi != nullptr;
-  if (radius == 4) {
-    dim3 block(kLookupPB * 4 * 9);
-    if (split) corr_lookup_kernel<4, true><<<grid, block, 0, s>>>(pv, c2, nullptr, out_hi, out_lo, out_stride, npix);
-    else corr_lookup_kernel<4, false><<<grid, block, 0, s>>>(pv, c2, out_f32, nullptr, nullptr, out_stride, npix);
-  } else if (radius == 3) {
-    dim3 block(kLookupPB * 4 * 7);
-    if (split) corr_lookup_kernel<3, true><<<grid, block, 0, s>>>(pv, c2, nullptr, out_hi, out_lo, out_stride, npix);
-    else corr_lookup_kernel<3, false><<<grid, block, 0, s>>>(pv, c2, out_f32, nullptr, nullptr, out_stride, npix);
-  } else {
-    set_error("radius %d unsupported (3 = raft-small, 4 = raft-things)", radius);
-    return RB_ERR_UNSUPPORTED;
+  RB_REQUIRE(radius == 3 || radius == 4, RB_ERR_UNSUPPORTED, "radius %d unsupported (3 = raft-small, 4 = raft-things)", radius);
+  RB_REQUIRE(out_hi == nullptr || out_stride % 8 == 0, RB_ERR_BAD_SHAPE, "lookup: split output stride %d not a multiple of 8",
+             out_stride);
+  const int npix = B * h * w;
+  PyramidMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int l = 0; l < RB_NUM_LEVELS; ++l) {
+    if (!pv.tma_ok[l]) continue;
+    uint64_t dims[3] = {(uint64_t)pv.wl[l], (uint64_t)pv.hl[l], (uint64_t)npix};
+    uint64_t str[2] = {(uint64_t)pv.wl[l] * 4, (uint64_t)pv.wl[l] * pv.hl[l] * 4};
+    uint32_t box[3] = {(uint32_t)kPatchCols, (uint32_t)(2 * radius + 3), 1};
+    if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_SW64) != RB_OK) pv.tma_ok[l] = 0;  // plain loads instead
   }
-  RB_CHECK_LAUNCH("corr_lookup_kernel");
-  return RB_OK;
+  const float2* c2 = reinterpret_cast<const float2*>(coords);
+  const bool split = out_hi != nullptr;
+  if (radius == 4)
+    return split ? launch_lookup_cfg<4, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
+                 : launch_lookup_cfg<4, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
+  return split ? launch_lookup_cfg<3, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
+               : launch_lookup_cfg<3, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
 }
 
 int corr_build_tc(const float* fmap1, const float* fmap2, float* pyramid, int B, int h, int w, int C,

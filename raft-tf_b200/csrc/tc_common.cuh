@@ -132,14 +132,15 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* a, uint32_t* b) {
 }
 
 // ---- host: tensor maps --------------------------------------------------------------------------------
-// fp16 tensor, up to 4 dims (innermost first), 128-byte swizzle, zero fill for out-of-bounds boxes.
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+// up to 4 dims (innermost first), zero fill for out-of-bounds boxes; kind selects element type and swizzle
+enum { TMAP_F16_SW128 = 0, TMAP_F32_SW64 = 1 };
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int kind);
 
 }  // namespace tc
 
 // per-thread cache of encoded tensor maps (conv_tc.cu)
 int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                const uint32_t* box);
+                const uint32_t* box, int kind = tc::TMAP_F16_SW128);
 
 }  // namespace rb
