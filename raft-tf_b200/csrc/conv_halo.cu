@@ -131,6 +131,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (grp + 1 < groups) issue_a(grp + 1);
       }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // every warp issues the PDL trigger once its part is done
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
@@ -163,6 +164,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       umma_commit(tmem_full_bar);
       if (dbg) dbg[4] = gtime_ns();
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else {
     const int q = warp & 3;
     constexpr int kColsPerWarp = BLOCK_N >= 128 ? 32 : (BLOCK_N == 96 ? 32 : 16);
@@ -173,6 +175,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int px = g.s_is_x ? si : fi, py = g.s_is_x ? fi : si;
     const bool valid = (py < p.h) && (px < p.w) && (si < s0 + g.q);
     const int pix = (b * p.h + py) * p.w + px;
+    if (grp >= kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (grp < kGroups) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -265,7 +268,11 @@ static int launch_halo_cfg(const ConvParams& p, const HaloGeom& g, const CUtenso
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // Programmatic dependent launch is OFF by default: measured on the update block (profiles/r01_notes.md) it hides
+  // the ~3.5 us launch gap but the dependents' CTAs then wait just as long for the grid-completion signal (early
+  // trigger: 222 us, trigger after the MMA loop: 220 us, no PDL: 217 us per step).  RAFT_B200_PDL=1 enables it.
+  static const int pdl = getenv("RAFT_B200_PDL") ? 1 : 0;
+  cfg.numAttrs = pdl;
   RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BLOCK_N>, maps[0], maps[1], maps[2], maps[3], p, g));
   RB_CHECK_LAUNCH("conv_halo_kernel");
   return RB_OK;

@@ -118,6 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
       }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // every warp issues the PDL trigger once its part is done
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
@@ -143,6 +144,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       umma_commit(tmem_full_bar);
       if (dbg) dbg[4] = gtime_ns();
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else {
     // ---- epilogue: warps 2..17 ----
     const int q = warp & 3;
@@ -153,6 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
     const bool valid = (py < p.h) && (px < p.w);
     const int pix = (b * p.h + py) * p.w + px;
+    if (grp >= kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (grp < kGroups) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -324,7 +327,11 @@ static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap*
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // Programmatic dependent launch is OFF by default: measured on the update block (profiles/r01_notes.md) it hides
+  // the ~3.5 us launch gap but the dependents' CTAs then wait just as long for the grid-completion signal (early
+  // trigger: 222 us, trigger after the MMA loop: 220 us, no PDL: 217 us per step).  RAFT_B200_PDL=1 enables it.
+  static const int pdl = getenv("RAFT_B200_PDL") ? 1 : 0;
+  cfg.numAttrs = pdl;
   int stages = Cfg::kStages;
   static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
   if (env_stages > 0 && env_stages < stages) stages = env_stages;
