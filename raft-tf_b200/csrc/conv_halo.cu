@@ -290,6 +290,10 @@ int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled) {
   // epilogues with MMA loops, which matters more there than operand traffic
   if (m_tiles > 2 * 148 && p.kh * p.kw * conv_chunks(p) <= 18 && p.cout <= 64) return RB_OK;
   const int bn = halo_block_n(p.cout, m_tiles);
+  // Same-box measurements (profiles/r01_notes.md): with a single wave of CTAs (batch 1) the halo kernel is ~2 % faster
+  // than the per-tap kernel; with several waves (batch 8: 6 waves) its two-stage A ring stalls at every tap-row boundary
+  // and it is 13 % slower (1317 vs 1142 us per update step) -- use it only for single-wave launches.
+  if (m_tiles * ((p.cout + bn - 1) / bn) > 148) return RB_OK;
   CUtensorMap maps[4];
   {
     const uint64_t C = (uint64_t)p.in_stride;

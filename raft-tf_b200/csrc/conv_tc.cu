@@ -352,7 +352,8 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
-  const int bn = choose_block_n(p.cout, m_tiles);
+  int bn = choose_block_n(p.cout, m_tiles);
+  if (getenv("RAFT_B200_FORCE_SHALLOW") && bn > 64 && m_tiles > 148) bn = 64;
   CUtensorMap maps[4];
   {
     uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
@@ -373,7 +374,9 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   }
   const long ctas = m_tiles * ((p.cout + bn - 1) / bn);
   const int kiters = p.kh * p.kw * conv_chunks(p);
-  const bool shallow = bn <= 64 && ctas > 2 * 148 && kiters <= 18;
+  static const bool force_shallow = getenv("RAFT_B200_FORCE_SHALLOW") != nullptr;  // experiment knob
+  bool shallow = bn <= 64 && ctas > 2 * 148 && kiters <= 18;
+  if (force_shallow && bn <= 64 && ctas > 148) shallow = true;
   switch (bn) {
     case 16: return shallow ? launch_cfg<16, true>(p, g, maps, s) : launch_cfg<16, false>(p, g, maps, s);
     case 32: return shallow ? launch_cfg<32, true>(p, g, maps, s) : launch_cfg<32, false>(p, g, maps, s);
