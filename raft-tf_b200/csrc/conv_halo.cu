@@ -286,9 +286,6 @@ int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled) {
   HaloGeom g;
   if (!halo_geom(p, &g)) return RB_OK;
   const long m_tiles = (long)p.B * g.tiles_f * g.tiles_s;
-  // many pixel tiles and a short K loop (encoder layers): the 2-CTA/SM shallow kernel of conv_tc.cu overlaps
-  // epilogues with MMA loops, which matters more there than operand traffic
-  if (m_tiles > 2 * 148 && p.kh * p.kw * conv_chunks(p) <= 18 && p.cout <= 64) return RB_OK;
   const int bn = halo_block_n(p.cout, m_tiles);
   // Same-box measurements (profiles/r01_notes.md): with a single wave of CTAs (batch 1) the halo kernel is ~2 % faster
   // than the per-tap kernel; with several waves (batch 8: 6 waves) its two-stage A ring stalls at every tap-row boundary

@@ -29,55 +29,58 @@ constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled
 constexpr int kATileBytes = kTileM * 128;  // 16 KB
 constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 
-// SHALLOW = 2 pipeline stages and two CTAs per SM: for convs with many pixel tiles and a short K loop
-// (the encoder layers) the epilogue of one CTA overlaps the MMA loop of its neighbour.  Otherwise
-// one CTA per SM with as many stages as fit (the single-wave, long-K convs of the update block).
-template <int BLOCK_N, bool SHALLOW>
+// PERSISTENT kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so CTAs that
+// run side by side share the same activation tile in L2).  The accumulators are double-buffered in TMEM
+// (2 x 2*BLOCK_N columns): the MMA warp starts the K loop of tile i+1 while the 16 epilogue warps drain tile i,
+// and the smem ring / its mbarrier phases simply continue across tiles.  With one wave of tiles (the update block
+// at batch 1) this degenerates to one tile per CTA; with many tiles (batched runs, encoder layers, the 3025-tile
+// correlation GEMM) the epilogue disappears behind the next tile's MMA loop.
+template <int BLOCK_N>
 struct TcCfg {
   static constexpr int kBTileBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-  static constexpr int kStages = SHALLOW ? 2 : ((200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes);
-  static constexpr int kMinBlocks = SHALLOW ? 2 : 1;
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : 256;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kAccCols = 2 * BLOCK_N;  // hi*hi | cross terms
+  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                   : (2 * kAccCols <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kColsPerWarp = BLOCK_N >= 96 ? 32 : 16;
+  static constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1 column groups of epilogue warps
 };
 
 struct TileGeom {
   int bw_log2, bh_log2;  // box = 2^bh x 2^bw pixels, product 128
   int tiles_x, tiles_y;  // per image
+  int n_tiles;           // cout tiles
+  int total_tiles;       // B * tiles_x * tiles_y * n_tiles
 };
 
-template <int BLOCK_N, bool SHALLOW>
-__global__ void __launch_bounds__(kTcThreads, (TcCfg<BLOCK_N, SHALLOW>::kMinBlocks))
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const ConvParams p, const TileGeom g, const int STAGES) {
-  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
+  using Cfg = TcCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
-  // tile coordinates
-  const int tiles_per_img = g.tiles_x * g.tiles_y;
-  const int b = blockIdx.x / tiles_per_img;
-  const int trem = blockIdx.x - b * tiles_per_img;
-  const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
-  const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2;
-  const int n0 = blockIdx.y * BLOCK_N;
   const int chunks = conv_chunks(p);
   const int taps = p.kh * p.kw;
   const int kiters = taps * chunks;
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], Cfg::kGroups * 4); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -86,98 +89,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: wait until everything this kernel depends on (the previous kernels' outputs) is complete and visible.
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
   if (dbg && threadIdx.x == 0) dbg[2] = gtime_ns();
 
   if (warp == 0) {
     if (lane == 0) {
       const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-      const int wb = p.w_per_batch ? b : 0;
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t phase = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
-        // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
-        // per-sample runs bit for bit.
-        const int cki = it / taps, tt = it - cki * taps;
-        const int ck = conv_chunk(p, cki);
-        const int kx = tt / p.kh, ky = tt - kx * p.kh;
-        const int t = ky * p.kw + kx;
-        const int dy = ky - ph, dx = kx - pw;
-        const int c0 = p.in_choff + ck * kChunkK;
-        tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
-        tma_load_4d(&tmA_lo, &full_bar[s], st + kATileBytes, c0, x0 + dx, y0 + dy, b);
-        const int kcol = t * p.cin_pad + ck * kChunkK;
-        tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
-        tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+      int git = 0;  // ring position, continues across tiles
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+        const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
+        const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
+        const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
+        const int wb = p.w_per_batch ? b : 0;
+        for (int it = 0; it < kiters; ++it, ++git) {
+          const int s = git % STAGES;
+          const uint32_t phase = (git / STAGES) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
+          // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
+          // per-sample runs bit for bit.
+          const int cki = it / taps, tt = it - cki * taps;
+          const int ck = conv_chunk(p, cki);
+          const int kx = tt / p.kh, ky = tt - kx * p.kh;
+          const int t = ky * p.kw + kx;
+          const int dy = ky - ph, dx = kx - pw;
+          const int c0 = p.in_choff + ck * kChunkK;
+          tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
+          tma_load_4d(&tmA_lo, &full_bar[s], st + kATileBytes, c0, x0 + dx, y0 + dy, b);
+          const int kcol = t * p.cin_pad + ck * kChunkK;
+          tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
+          tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+        }
       }
     }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // every warp issues the PDL trigger once its part is done
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
       constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t phase = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], phase);
+      int git = 0, li = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++li) {
+        const int ab = li & 1;
+        mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
-        if (dbg && it == 0) dbg[3] = gtime_ns();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t a_hi = umma_desc_sw128(st);
-        const uint64_t a_lo = umma_desc_sw128(st + kATileBytes);
-        const uint64_t b_all = umma_desc_sw128(st + 2 * kATileBytes);  // [B_hi ; B_lo], 2N rows
+        const uint32_t acc = tmem_base + ab * Cfg::kAccCols;
+        for (int it = 0; it < kiters; ++it, ++git) {
+          const int s = git % STAGES;
+          const uint32_t phase = (git / STAGES) & 1;
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          if (dbg && git == 0) dbg[3] = gtime_ns();
+          const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t a_hi = umma_desc_sw128(st);
+          const uint64_t a_lo = umma_desc_sw128(st + kATileBytes);
+          const uint64_t b_all = umma_desc_sw128(st + 2 * kATileBytes);  // [B_hi ; B_lo], 2N rows
 #pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k) {
-          const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per k-slice, in 16-byte units
-          umma_f16(tmem_base, a_hi + koff, b_all + koff, idesc_2n, (it | k) != 0);
-          umma_f16(tmem_base + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
+          for (int k = 0; k < kChunkK / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per k-slice, in 16-byte units
+            umma_f16(acc, a_hi + koff, b_all + koff, idesc_2n, (it | k) != 0);
+            umma_f16(acc + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+        umma_commit(&tmem_full_bar[ab]);
+        if (dbg && li == 0) dbg[4] = gtime_ns();
       }
-      umma_commit(tmem_full_bar);
-      if (dbg) dbg[4] = gtime_ns();
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else {
-    // ---- epilogue: warps 2..17 ----
+    // ---- epilogue: warps 2..17 -- lane quarter (warp % 4), column group (warp - 2) / 4 ----
     const int q = warp & 3;
-    constexpr int kColsPerWarp = BLOCK_N >= 128 ? 32 : (BLOCK_N == 96 ? 32 : 16);
-    constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1
     const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // tile row = pixel index inside the box
-    const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
-    const bool valid = (py < p.h) && (px < p.w);
-    const int pix = (b * p.h + py) * p.w + px;
-    if (grp >= kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (grp < kGroups) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-      // PDL trigger: only now (MMA loop done, epilogue starting) may the next kernel's CTAs be scheduled -- triggering
-      // at kernel start let them take the SMs this kernel's own late CTAs were waiting for (phase_times.py).
-      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-      if (dbg && warp == 2 && lane == 0) dbg[5] = gtime_ns();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (grp >= Cfg::kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (grp < Cfg::kGroups) {
+      int li = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++li) {
+        const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+        const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
+        const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
+        const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
+        const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
+        const bool valid = (py < p.h) && (px < p.w);
+        const int pix = (b * p.h + py) * p.w + px;
+        const int ab = li & 1;
+        mbar_wait(&tmem_full_bar[ab], (li >> 1) & 1);
+        tc_fence_after();
+        if (li == 0) {
+          asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+          if (dbg && warp == 2 && lane == 0) dbg[5] = gtime_ns();
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ab * Cfg::kAccCols;
 #pragma unroll 1
-      for (int cc = 0; cc < kColsPerWarp; cc += 16) {
-        const int c = grp * kColsPerWarp + cc;
-        if (n0 + c >= p.cout) break;  // warp-uniform
-        uint32_t d0[16], d1[16];
-        tmem_ld16(trow + c, d0);
-        tmem_ld16(trow + BLOCK_N + c, d1);
-        tmem_ld_wait(d0, d1);
-        float v[16];
+        for (int cc = 0; cc < Cfg::kColsPerWarp; cc += 16) {
+          const int c = grp * Cfg::kColsPerWarp + cc;
+          if (n0 + c >= p.cout) break;  // warp-uniform
+          uint32_t d0[16], d1[16];
+          tmem_ld16(trow + c, d0);
+          tmem_ld16(trow + BLOCK_N + c, d1);
+          tmem_ld_wait(d0, d1);
+          float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
-        if (valid) {
-          epilogue_store<8>(p, pix, n0 + c, v);
-          epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
+          if (valid) {
+            epilogue_store<8>(p, pix, n0 + c, v);
+            epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+          }
+        }
+        // this warp no longer needs the accumulator buffer: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[ab])) : "memory");
         }
       }
     }
@@ -308,18 +336,23 @@ static int choose_block_n(int cout, long m_tiles) {
   return best;
 }
 
-template <int BLOCK_N, bool SHALLOW>
-static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap* maps, cudaStream_t s) {
-  using Cfg = TcCfg<BLOCK_N, SHALLOW>;
+template <int BLOCK_N>
+static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
+  using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
+  static int num_sms = 148;
   if (!attr_set) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, SHALLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    int dev = 0;
+    RB_CHECK_CUDA(cudaGetDevice(&dev));
+    RB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
+  g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  g.total_tiles = p.B * g.tiles_x * g.tiles_y * g.n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(p.B * g.tiles_x * g.tiles_y, (p.cout + BLOCK_N - 1) / BLOCK_N);
+  cfg.gridDim = dim3(g.total_tiles < num_sms ? g.total_tiles : num_sms);  // persistent: at most one CTA per SM
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
@@ -335,7 +368,7 @@ static int launch_cfg(const ConvParams& p, const TileGeom& g, const CUtensorMap*
   int stages = Cfg::kStages;
   static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
   if (env_stages > 0 && env_stages < stages) stages = env_stages;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, SHALLOW>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
@@ -352,8 +385,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
-  int bn = choose_block_n(p.cout, m_tiles);
-  if (getenv("RAFT_B200_FORCE_SHALLOW") && bn > 64 && m_tiles > 148) bn = 64;
+  const int bn = choose_block_n(p.cout, m_tiles);
   CUtensorMap maps[4];
   {
     uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
@@ -372,17 +404,12 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
     if ((rc = cached_tmap(&maps[2], p.w_hi, 3, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
   }
-  const long ctas = m_tiles * ((p.cout + bn - 1) / bn);
-  const int kiters = p.kh * p.kw * conv_chunks(p);
-  static const bool force_shallow = getenv("RAFT_B200_FORCE_SHALLOW") != nullptr;  // experiment knob
-  bool shallow = bn <= 64 && ctas > 2 * 148 && kiters <= 18;
-  if (force_shallow && bn <= 64 && ctas > 148) shallow = true;
   switch (bn) {
-    case 16: return shallow ? launch_cfg<16, true>(p, g, maps, s) : launch_cfg<16, false>(p, g, maps, s);
-    case 32: return shallow ? launch_cfg<32, true>(p, g, maps, s) : launch_cfg<32, false>(p, g, maps, s);
-    case 64: return shallow ? launch_cfg<64, true>(p, g, maps, s) : launch_cfg<64, false>(p, g, maps, s);
-    case 96: return launch_cfg<96, false>(p, g, maps, s);
-    default: return launch_cfg<128, false>(p, g, maps, s);
+    case 16: return launch_cfg<16>(p, g, maps, s);
+    case 32: return launch_cfg<32>(p, g, maps, s);
+    case 64: return launch_cfg<64>(p, g, maps, s);
+    case 96: return launch_cfg<96>(p, g, maps, s);
+    default: return launch_cfg<128>(p, g, maps, s);
   }
 }
 
