@@ -129,7 +129,8 @@ __global__ void enc_gather_kernel(const float* __restrict__ img, const __half* _
   out_lo[i] = lo;
 }
 
-// Stem gather (7x7 stride 2 over the 3-channel image): 8 consecutive k per thread, 16-byte stores.
+// Stem gather (7x7 stride 2 over the 3-channel image): 8 consecutive k per thread, 16-byte stores.  The (ky,kx,ci)
+// triple is advanced incrementally (r01 profile: the div/mod version was the largest single encoder kernel).
 __global__ void enc_gather_img8_kernel(const float* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                        int B, int H, int W, int cin, int k, int s, int pt, int pl, int oh, int ow, int kpad) {
   const int K = k * k * cin, k8 = kpad / 8;
@@ -138,22 +139,17 @@ __global__ void enc_gather_img8_kernel(const float* __restrict__ img, __half* __
   const int kk0 = (i % k8) * 8;
   size_t px = i / k8;
   const int ox = px % ow, oy = (px / ow) % oh, b = px / ((size_t)ow * oh);
+  int ci = kk0 % cin, t = kk0 / cin, kx = t % k, ky = t / k;
+  const int iy0 = oy * s - pt, ix0 = ox * s - pl;
+  const float* base = img + (size_t)b * H * W * cin;
   __align__(16) __half hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int kk = kk0 + j;
-    float v = 0.f;
-    bool in = false;
-    if (kk < K) {
-      const int ci = kk % cin, t = kk / cin, kx = t % k, ky = t / k;
-      const int iy = oy * s + ky - pt, ix = ox * s + kx - pl;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        v = 2.0f * __ldg(img + ((size_t)(b * H + iy) * W + ix) * cin + ci) - 1.0f;  // RAFT.py:53-59
-        in = true;
-      }
-    }
-    if (in) split_f32(v, hi[j], lo[j]);
+    const int iy = iy0 + ky, ix = ix0 + kx;
+    const bool in = (kk0 + j < K) && iy >= 0 && iy < H && ix >= 0 && ix < W;
+    if (in) split_f32(2.0f * __ldg(base + ((size_t)iy * W + ix) * cin + ci) - 1.0f, hi[j], lo[j]);  // RAFT.py:53-59
     else hi[j] = lo[j] = __float2half_rn(0.f);  // SAME zero padding is applied AFTER the 2x-1 preprocessing
+    if (++ci == cin) { ci = 0; if (++kx == k) { kx = 0; ++ky; } }
   }
   *reinterpret_cast<uint4*>(out_hi + px * kpad + kk0) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(out_lo + px * kpad + kk0) = *reinterpret_cast<const uint4*>(lo);
