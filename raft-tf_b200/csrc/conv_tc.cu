@@ -52,10 +52,14 @@ struct TileGeom {
   int bw_log2, bh_log2;  // box = 2^bh x 2^bw pixels, product 128
   int tiles_x, tiles_y;  // per image
   int n_tiles;           // cout tiles
-  int total_tiles;       // B * tiles_x * tiles_y * n_tiles
+  int m_tiles;           // B * tiles_x * tiles_y pixel tiles
+  int total_tiles;       // work items: m_tiles * n_tiles, or ceil(m_tiles/2) * n_tiles PAIRS in cluster mode
 };
 
-template <int BLOCK_N>
+// PAIR = true: CTAs are launched as clusters of two that work on two pixel tiles of the SAME cout tile; CTA 0 fetches
+// B_hi, CTA 1 fetches B_lo, each with TMA multicast into both CTAs' shared memory, so every SM issues only half of
+// the weight-tile requests (the measured bound of the MMA loop is the ~38 B/clk a single SM can request from L2).
+template <int BLOCK_N, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -79,7 +83,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], Cfg::kGroups * 4); }
     fence_barrier_init();
     fence_proxy_async();
@@ -87,8 +91,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything of ours can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
+  const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
@@ -98,12 +106,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
       int git = 0;  // ring position, continues across tiles
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+      for (int tile = first; tile < g.total_tiles; tile += stride) {
+        const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
+        const int mt = PAIR ? 2 * mq + rank : mq;  // a trailing odd tile gets a dummy partner: b >= B, TMA zero-fills
         const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
         const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
-        const int wb = p.w_per_batch ? b : 0;
+        const int wb = p.w_per_batch ? min(b, p.B - 1) : 0;
         for (int it = 0; it < kiters; ++it, ++git) {
           const int s = git % STAGES;
           const uint32_t phase = (git / STAGES) & 1;
@@ -122,8 +131,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
           tma_load_4d(&tmA_lo, &full_bar[s], st + kATileBytes, c0, x0 + dx, y0 + dy, b);
           const int kcol = t * p.cin_pad + ck * kChunkK;
-          tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
-          tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+          if (PAIR) {  // half of the weight tile each, delivered to both CTAs
+            if (rank == 0) tma_load_3d_mc(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb, (uint16_t)3);
+            else tma_load_3d_mc(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb, (uint16_t)3);
+          } else {
+            tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
+            tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+          }
         }
       }
     }
@@ -133,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
       constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
       int git = 0, li = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++li) {
+      for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int ab = li & 1;
         mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
@@ -154,7 +168,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             umma_f16(acc, a_hi + koff, b_all + koff, idesc_2n, (it | k) != 0);
             umma_f16(acc + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          if (PAIR) umma_commit_mc(&empty_bar[s], (uint16_t)3);  // both producers write into this stage of both CTAs
+          else umma_commit(&empty_bar[s]);                      // frees the smem stage when these MMAs retire
         }
         umma_commit(&tmem_full_bar[ab]);
         if (dbg && li == 0) dbg[4] = gtime_ns();
@@ -169,13 +184,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (grp >= Cfg::kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (grp < Cfg::kGroups) {
       int li = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++li) {
-        const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+      for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
+        const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
+        const int mt = PAIR ? 2 * mq + rank : mq;
         const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
         const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
         const int py = y0 + (r >> g.bw_log2), px = x0 + (r & ((1 << g.bw_log2) - 1));
-        const bool valid = (py < p.h) && (px < p.w);
+        const bool valid = (py < p.h) && (px < p.w) && (mt < g.m_tiles);
         const int pix = (b * p.h + py) * p.w + px;
         const int ab = li & 1;
         mbar_wait(&tmem_full_bar[ab], (li >> 1) & 1);
@@ -213,6 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (dbg && warp == 2 && lane == 0) dbg[6] = gtime_ns();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (dbg && threadIdx.x == 0) dbg[7] = gtime_ns();
   if (warp == 1) {
     tc_fence_after();
@@ -336,39 +353,45 @@ static int choose_block_n(int cout, long m_tiles) {
   return best;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     int dev = 0;
     RB_CHECK_CUDA(cudaGetDevice(&dev));
     RB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
   g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
-  g.total_tiles = p.B * g.tiles_x * g.tiles_y * g.n_tiles;
+  g.m_tiles = p.B * g.tiles_x * g.tiles_y;
+  g.total_tiles = (PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(g.total_tiles < num_sms ? g.total_tiles : num_sms);  // persistent: at most one CTA per SM
+  const int units = PAIR ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
+  cfg.gridDim = dim3((g.total_tiles < units ? g.total_tiles : units) * (PAIR ? 2 : 1));
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   // Programmatic dependent launch is OFF by default: measured on the update block (profiles/r01_notes.md) it hides
   // the ~3.5 us launch gap but the dependents' CTAs then wait just as long for the grid-completion signal (early
   // trigger: 222 us, trigger after the MMA loop: 220 us, no PDL: 217 us per step).  RAFT_B200_PDL=1 enables it.
   static const int pdl = getenv("RAFT_B200_PDL") ? 1 : 0;
-  cfg.numAttrs = pdl;
+  cfg.numAttrs = 1 + pdl;
   int stages = Cfg::kStages;
   static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
   if (env_stages > 0 && env_stages < stages) stages = env_stages;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, PAIR>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
@@ -404,12 +427,22 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
     if ((rc = cached_tmap(&maps[2], p.w_hi, 3, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
   }
+  static const bool pair = getenv("RAFT_B200_PAIR") != nullptr;  // experiment: cluster-of-2 weight multicast
+  if (pair && m_tiles >= 2) {
+    switch (bn) {
+      case 16: return launch_cfg<16, true>(p, g, maps, s);
+      case 32: return launch_cfg<32, true>(p, g, maps, s);
+      case 64: return launch_cfg<64, true>(p, g, maps, s);
+      case 96: return launch_cfg<96, true>(p, g, maps, s);
+      default: return launch_cfg<128, true>(p, g, maps, s);
+    }
+  }
   switch (bn) {
-    case 16: return launch_cfg<16>(p, g, maps, s);
-    case 32: return launch_cfg<32>(p, g, maps, s);
-    case 64: return launch_cfg<64>(p, g, maps, s);
-    case 96: return launch_cfg<96>(p, g, maps, s);
-    default: return launch_cfg<128>(p, g, maps, s);
+    case 16: return launch_cfg<16, false>(p, g, maps, s);
+    case 32: return launch_cfg<32, false>(p, g, maps, s);
+    case 64: return launch_cfg<64, false>(p, g, maps, s);
+    case 96: return launch_cfg<96, false>(p, g, maps, s);
+    default: return launch_cfg<128, false>(p, g, maps, s);
   }
 }
 
