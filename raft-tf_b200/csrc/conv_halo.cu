@@ -280,8 +280,11 @@ static int launch_halo_cfg(const ConvParams& p, const HaloGeom& g, const CUtenso
 
 int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled) {
   *handled = false;
-  static const bool disabled = getenv("RAFT_B200_NO_HALO") != nullptr;
-  if (disabled) return RB_OK;
+  // Opt-in (RAFT_B200_HALO=1).  Same-box A/B on the update block at batch 1 (profiles/r01_notes.md): 236.6 us with the
+  // halo kernel for every multi-tap conv, 236.1 us with the persistent per-tap kernel -- the activation re-fetches it
+  // removes are not what bounds the MMA loop (the weight tiles are), and at several waves it is 13 % slower.
+  static const bool enabled = getenv("RAFT_B200_HALO") != nullptr && getenv("RAFT_B200_NO_HALO") == nullptr;
+  if (!enabled) return RB_OK;
   if (p.cin_pad % 64 || p.in_stride % 8 || p.in_choff % 8) return RB_OK;
   HaloGeom g;
   if (!halo_geom(p, &g)) return RB_OK;
@@ -291,6 +294,8 @@ int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled) {
   // than the per-tap kernel; with several waves (batch 8: 6 waves) its two-stage A ring stalls at every tap-row boundary
   // and it is 13 % slower (1317 vs 1142 us per update step) -- use it only for single-wave launches.
   if (m_tiles * ((p.cout + bn - 1) / bn) > 148) return RB_OK;
+  static const int min_n = getenv("RAFT_B200_HALO_MIN_N") ? atoi(getenv("RAFT_B200_HALO_MIN_N")) : 0;  // tuning knob
+  if (bn < min_n) return RB_OK;
   CUtensorMap maps[4];
   {
     const uint64_t C = (uint64_t)p.in_stride;
