@@ -43,3 +43,22 @@ def flow_to_color(flow_uv, clip_flow=None, convert_to_bgr=False):
         col = np.where(inside, 1 - rad * (1 - col), col * 0.75)
         img[..., 2 - ch if convert_to_bgr else ch] = np.floor(255 * col)
     return img
+
+
+def write_flo(path, flow_uv):
+    """Middlebury .flo file (magic 202021.25, int32 width, int32 height, float32 [H,W,2] row-major u,v) -- the
+    format of the reference's unused writer (flow_utils.py:302-318)."""
+    f = np.ascontiguousarray(flow_uv, dtype=np.float32)
+    assert f.ndim == 3 and f.shape[2] == 2
+    with open(path, "wb") as fh:
+        np.array([202021.25], np.float32).tofile(fh)
+        np.array([f.shape[1], f.shape[0]], np.int32).tofile(fh)
+        f.tofile(fh)
+
+
+def read_flo(path):
+    with open(path, "rb") as fh:
+        magic = np.fromfile(fh, np.float32, 1)[0]
+        assert abs(magic - 202021.25) < 1e-3, "not a .flo file"
+        w, h = np.fromfile(fh, np.int32, 2)
+        return np.fromfile(fh, np.float32, 2 * int(w) * int(h)).reshape(int(h), int(w), 2)

@@ -48,13 +48,14 @@ def main(argv=None):
     p.add_argument('--iters', type=int, default=20, help='extension: GRU iterations (reference: 20)')
     p.add_argument('--keep-size', action='store_true', help='extension: pad to a multiple of 8 instead of resizing to 432x1024')
     p.add_argument('--npy', default=None, help='extension: also save the raw [H,W,2] flow')
+    p.add_argument('--flo', default=None, help='extension: also save the flow as a Middlebury .flo file')
     args = p.parse_args(argv)
     if args.mode != 'test':
         print(f"mode '{args.mode}' has no implementation in the reference either (infer_raft.py:71-95); nothing to do")
         return 0
     from networks import RAFT
     import cv2
-    from flow_utils import flow_to_color
+    from flow_utils import flow_to_color, write_flo
     left, right = read_pair(args.im1, args.im2, None if args.keep_size else (432, 1024))
     model = RAFT.RAFT(left.shape[1:], args, iters=args.iters).load(args.load)
     flow = model.forward(left, right).cpu().numpy()
@@ -62,6 +63,8 @@ def main(argv=None):
     cv2.imwrite("raft_flow_raft-things.png", flow_to_color(flow[0], convert_to_bgr=True))
     if args.npy:
         np.save(args.npy, flow[0])
+    if args.flo:
+        write_flo(args.flo, flow[0])
     return 0
 
 
