@@ -112,41 +112,53 @@ struct PyramidMaps {
   CUtensorMap m[RB_NUM_LEVELS];  // (W_l, H_l, B*N) fp32, box (16, 2r+3, 1), 64-byte swizzle
 };
 
-constexpr int kLookupPB = 8;     // pixels per block
+constexpr int kLookupPB = 16;    // pixels per block: 440 blocks of 576 threads at 440x1024 = ONE wave at 3 blocks/SM
 constexpr int kPatchCols = 16;   // staged columns per row (64 bytes)
-constexpr int kUnitBytes = 1024; // shared bytes reserved per unit (>= (2r+3)*64, keeps the swizzle phase at 0)
+constexpr int kUnitBytes = 768;  // shared bytes per unit (>= (2r+3)*64); a multiple of 128 so the swizzle phase is known
 
-// float index of element (row, col) inside a unit's staged patch (CU_TENSOR_MAP_SWIZZLE_64B: the 16-byte chunk
-// index is XORed with bits [1,3) of the 64-byte row index)
-__device__ __forceinline__ int patch_idx(int row, int col) {
-  return row * kPatchCols + ((((col >> 2) ^ (row >> 1)) & 3) << 2) + (col & 3);
+// float index of element (row, col) inside a unit's staged patch.  CU_TENSOR_MAP_SWIZZLE_64B XORs the 16-byte chunk
+// index with bits [7,9) of the shared-memory byte address = (slot_base/128 + row/2) & 3; `phase` = (slot_base/128) & 3.
+__device__ __forceinline__ int patch_idx(int row, int col, int phase) {
+  return row * kPatchCols + ((((col >> 2) ^ ((row >> 1) + phase)) & 3) << 2) + (col & 3);
 }
+
+template <int R>
+struct LookupSmem {
+  static constexpr int D = 2 * R + 1, K = D * D, UNITS = kLookupPB * 4;
+  static constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel and plane (324 -> 328, 196 -> 200)
+  static constexpr int kPatchOff = 0;
+  static constexpr int kXtabOff = UNITS * kUnitBytes;              // float2 [UNITS][D]: (qx, packed ax0 | ax1 << 8)
+  static constexpr int kOutOff = kXtabOff + UNITS * D * 8;         // half [PB][2][OUTP]
+  static constexpr int kBaseOff = kOutOff + kLookupPB * 2 * OUTP * 2;  // int [UNITS][2]: bx4, by
+  static constexpr int kBarOff = kBaseOff + UNITS * 8;
+  static constexpr int kBytes = kBarOff + 16;
+};
 
 template <int R, bool SPLIT>
 __global__ void __launch_bounds__(kLookupPB * 4 * (2 * R + 1))
 corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMaps maps,
                    const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
                    __half* __restrict__ out_lo, int out_stride, int npix) {
-  constexpr int D = 2 * R + 1, K = D * D, P = D + 2, UNITS = kLookupPB * 4, NT = UNITS * D;
-  constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel and plane (324 -> 328, 196 -> 200)
-  extern __shared__ __align__(1024) uint8_t lk_smem[];
-  float* patch = reinterpret_cast<float*>(lk_smem);                                    // [UNITS][256 floats]
-  float4* xtab = reinterpret_cast<float4*>(lk_smem + UNITS * kUnitBytes);             // [UNITS][D]
-  __half* ostage = reinterpret_cast<__half*>(lk_smem + UNITS * kUnitBytes + UNITS * D * 16);  // [PB][2][OUTP]
-  __shared__ int ubase[UNITS][2];  // bx4, by per unit
-  __shared__ __align__(8) uint64_t bar;
+  using L = LookupSmem<R>;
+  constexpr int D = L::D, K = L::K, P = D + 2, UNITS = L::UNITS, NT = UNITS * D, OUTP = L::OUTP;
+  extern __shared__ __align__(1024) uint8_t lk_smem[];  // no static shared memory in this kernel: the slots start at 0
+  float* patch = reinterpret_cast<float*>(lk_smem + L::kPatchOff);
+  float2* xtab = reinterpret_cast<float2*>(lk_smem + L::kXtabOff);
+  __half* ostage = reinterpret_cast<__half*>(lk_smem + L::kOutOff);
+  int* ubase = reinterpret_cast<int*>(lk_smem + L::kBaseOff);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lk_smem + L::kBarOff);
   const int tid = threadIdx.x;
   const int pix0 = blockIdx.x * kLookupPB;
 
-  if (tid == 0 && (tc::smem_u32(lk_smem) & 1023u)) __trap();  // the swizzle phase assumes 1024-byte aligned unit slots
+  if (tid == 0 && (tc::smem_u32(lk_smem) & 1023u)) __trap();  // the swizzle phase assumes 1024-byte aligned slot 0
   int n_tma = 0;
 #pragma unroll
   for (int l = 0; l < 4; ++l) n_tma += pv.tma_ok[l] ? kLookupPB : 0;
   if (tid == 0) {
-    tc::mbar_init(&bar, 1);
+    tc::mbar_init(bar, 1);
     tc::fence_barrier_init();
     tc::fence_proxy_async();
-    if (n_tma) tc::mbar_arrive_expect_tx(&bar, (uint32_t)(n_tma * P * kPatchCols * 4));
+    if (n_tma) tc::mbar_arrive_expect_tx(bar, (uint32_t)(n_tma * P * kPatchCols * 4));
   }
   if (SPLIT) {  // channel padding of the staged output rows (never produced by a tap)
     for (int e = tid; e < kLookupPB * 2 * (OUTP - 4 * K); e += NT) {
@@ -165,9 +177,9 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
     const float xf0 = __fadd_rn(c.x * inv, (float)(-R)), yf0 = __fadd_rn(c.y * inv, (float)(-R));
     const int bx4 = min(max((int)xf0, 0), W - 1) & ~3;
     const int by = min(max((int)yf0, 0), H - 1);
-    ubase[u][0] = bx4;
-    ubase[u][1] = by;
-    if (pv.tma_ok[lvl]) tc::tma_load_3d(&maps.m[lvl], &bar, lk_smem + u * kUnitBytes, bx4, by, pix);
+    ubase[2 * u] = bx4;
+    ubase[2 * u + 1] = by;
+    if (pv.tma_ok[lvl]) tc::tma_load_3d(&maps.m[lvl], bar, lk_smem + u * kUnitBytes, bx4, by, pix);
   }
   __syncthreads();
   // ---- fallback staging for levels TMA cannot address (W % 4 != 0) -------------------------------------------
@@ -178,12 +190,12 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
       if (pv.tma_ok[lvl]) continue;
       const int pix = min(pix0 + (u >> 2), npix - 1);
       const int H = pv.hl[lvl], W = pv.wl[lvl];
-      const int yy = min(ubase[u][1] + py, H - 1), col = ubase[u][0] + ch * 4;
+      const int yy = min(ubase[2 * u + 1] + py, H - 1), col = ubase[2 * u] + ch * 4;
       const float* row = pv.base[lvl] + ((size_t)pix * H + yy) * W;
       float4 v;
       v.x = __ldg(row + min(col + 0, W - 1)); v.y = __ldg(row + min(col + 1, W - 1));
       v.z = __ldg(row + min(col + 2, W - 1)); v.w = __ldg(row + min(col + 3, W - 1));
-      *reinterpret_cast<float4*>(&patch[u * (kUnitBytes / 4) + patch_idx(py, ch * 4)]) = v;  // a chunk stays contiguous
+      *reinterpret_cast<float4*>(&patch[u * (kUnitBytes / 4) + patch_idx(py, ch * 4, (u * (kUnitBytes / 128)) & 3)]) = v;
     }
   }
   // ---- phase 1: separable index math ---------------------------------------------------------------------------
@@ -202,9 +214,9 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
     x0 = min(max(x0, 0), W - 1);
     x1 = min(max(x1, 0), W - 1);
     const float qx = __fsub_rn((float)x1, x);  // utils.py:84 (clamped x1)
-    const int bx4 = ubase[u][0];
+    const int bx4 = ubase[2 * u];
     const int ax0 = min(max(x0 - bx4, 0), kPatchCols - 1), ax1 = min(max(x1 - bx4, 0), kPatchCols - 1);
-    xtab[u * D + j] = make_float4(qx, __fsub_rn(1.0f, qx), __int_as_float(ax0), __int_as_float(ax1));
+    xtab[u * D + j] = make_float2(qx, __int_as_float(ax0 | (ax1 << 8)));
   }
   const float y = __fadd_rn(cy, (float)(j - R));
   int y0 = (int)y;
@@ -212,21 +224,23 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   y0 = min(max(y0, 0), H - 1);
   y1 = min(max(y1, 0), H - 1);
   const float qy = __fsub_rn((float)y1, y), pyw = __fsub_rn(1.0f, qy);  // utils.py:85
-  const int by = ubase[u][1];
+  const int by = ubase[2 * u + 1];
   const int r0 = min(max(y0 - by, 0), P - 1), r1 = min(max(y1 - by, 0), P - 1);
   const float* pu = patch + u * (kUnitBytes / 4);
-  const int r0b = r0 * kPatchCols, r0x = (r0 >> 1) & 3, r1b = r1 * kPatchCols, r1x = (r1 >> 1) & 3;
-  __syncthreads();                       // xtab + fallback patches visible
-  if (n_tma) tc::mbar_wait(&bar, 0);     // TMA patches landed
+  const int phase = (u * (kUnitBytes / 128)) & 3;
+  const int r0b = r0 * kPatchCols, r0x = ((r0 >> 1) + phase) & 3, r1b = r1 * kPatchCols, r1x = ((r1 >> 1) + phase) & 3;
+  __syncthreads();                     // xtab + fallback patches visible
+  if (n_tma) tc::mbar_wait(bar, 0);    // TMA patches landed
   // ---- phase 2: taps of window row j ------------------------------------------------------------------------------
   const bool live = pix < npix;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    const float4 xt = xtab[u * D + i];
-    const int ax0 = __float_as_int(xt.z), ax1 = __float_as_int(xt.w);
+    const float2 xt = xtab[u * D + i];
+    const int packed = __float_as_int(xt.y), ax0 = packed & 0xff, ax1 = packed >> 8;
     const int c0h = ax0 >> 2, c0l = ax0 & 3, c1h = ax1 >> 2, c1l = ax1 & 3;
+    const float pxw = __fsub_rn(1.0f, xt.x);
     const float wa = __fmul_rn(xt.x, qy), wb = __fmul_rn(xt.x, pyw);  // utils.py:86-89
-    const float wc = __fmul_rn(xt.y, qy), wd = __fmul_rn(xt.y, pyw);
+    const float wc = __fmul_rn(pxw, qy), wd = __fmul_rn(pxw, pyw);
     const float Ia = pu[r0b + (((c0h ^ r0x) & 3) << 2) + c0l], Ib = pu[r1b + (((c0h ^ r1x) & 3) << 2) + c0l];
     const float Ic = pu[r0b + (((c1h ^ r0x) & 3) << 2) + c1l], Id = pu[r1b + (((c1h ^ r1x) & 3) << 2) + c1l];
     const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
@@ -296,8 +310,7 @@ int pyramid_view(const float* pyramid, int B, int h, int w, PyramidView* pv) {
 
 template <int R>
 static size_t lookup_smem_bytes() {
-  constexpr int D = 2 * R + 1, K = D * D, OUTP = (4 * K + 7) / 8 * 8, UNITS = kLookupPB * 4;
-  return (size_t)UNITS * kUnitBytes + (size_t)UNITS * D * 16 + (size_t)kLookupPB * 2 * OUTP * 2;
+  return (size_t)LookupSmem<R>::kBytes;
 }
 
 template <int R, bool SPLIT>
