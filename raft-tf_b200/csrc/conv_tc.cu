@@ -397,6 +397,7 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
 }
 
 int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled);
+int launch_conv_tc2(const ConvParams& p, cudaStream_t s, int bn, int bw_log2, int bh_log2, int tiles_x, int tiles_y, bool* handled);
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   if (p.kh * p.kw > 1) {  // multi-tap convs: halo-tile kernel (each input pixel is fetched once per tap ROW, not per tap)
@@ -409,6 +410,11 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
   const int bn = choose_block_n(p.cout, m_tiles);
+  {
+    bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
+    int rc = launch_conv_tc2(p, s, bn, g.bw_log2, g.bh_log2, g.tiles_x, g.tiles_y, &handled);
+    if (rc || handled) return rc;
+  }
   CUtensorMap maps[4];
   {
     uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
