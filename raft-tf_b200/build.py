@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "corr.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc2.cu", "conv_halo.cu", "conv_api.cu", "gemm_tc.cu", "update.cu", "upsample.cu", "encoder.cu"]
+SOURCES = ["capi.cu", "corr.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc2.cu", "update_fused.cu", "conv_halo.cu", "conv_api.cu", "gemm_tc.cu", "update.cu", "upsample.cu", "encoder.cu"]
 LIB = os.path.join(HERE, "lib", "libraft_b200.so")
 
 

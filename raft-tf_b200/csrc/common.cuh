@@ -117,6 +117,41 @@ __device__ __forceinline__ float tanh_f(float x) {  // 1 - 2/(1+e^{2x}); exact l
   return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  The tensor-core epilogues have one pixel per lane, so every lane
+// of a warp-wide access touches a different 32-byte sector: 256-bit accesses fill the sector a lane touches instead of
+// half of it and halve the number of LSU transactions of the epilogue (profiles/r01_notes.md).  32-byte aligned.
+__device__ __forceinline__ void ld256(const float* src, float* d) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7])
+               : "l"(src) : "memory");
+}
+__device__ __forceinline__ void ld256_nc(const float* src, float* d) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7])
+               : "l"(src));
+}
+__device__ __forceinline__ void st256(float* dst, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st256_b32(void* dst, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// All destinations / operands of the conv are 32-byte aligned at 16-channel granularity (uniform per launch).
+__device__ __forceinline__ bool epilogue_wide_ok(const ConvParams& p) {
+  bool ok = (p.cout & 15) == 0;
+  if (p.epi == EPI_ACT) {
+    ok = ok && ((p.d0_stride | p.d0_choff) & 15) == 0;
+    if (p.d1_hi) ok = ok && ((p.d1_stride | p.d1_choff) & 15) == 0;
+  } else if (p.epi == EPI_ZR || p.epi == EPI_Q) {
+    ok = ok && ((p.d0_stride | p.d0_choff) & 15) == 0 && (p.hidden & 15) == 0;
+  } else if (p.epi == EPI_DELTA) {
+    ok = false;
+  }
+  return ok;
+}
+
 // Store NV consecutive output channels [c, c+NV) of pixel `pix`; v holds acc (bias not yet added).
 // c is a multiple of NV; channel offsets of every destination are multiples of 8.
 template <int NV>
@@ -128,7 +163,13 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
   const bool full = (c + NV <= p.cout);
   if (p.addend) {
     const float* ad = p.addend + (size_t)pix * p.cout + c;
-    if (full && NV % 4 == 0 && (p.cout & 3) == 0) {
+    if constexpr (NV == 16) {  // wide path: the caller checked epilogue_wide_ok()
+      float t[16];
+      ld256_nc(ad, t);
+      ld256_nc(ad + 8, t + 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y[i] += t[i];
+    } else if (full && NV % 4 == 0 && (p.cout & 3) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(ad + i));
@@ -141,7 +182,10 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
   }
 
   auto load_f32 = [&](const float* src, float* dst) {  // NV consecutive floats, 4*NV-byte aligned
-    if constexpr (NV % 4 == 0) {
+    if constexpr (NV == 16) {
+      ld256(src, dst);
+      ld256(src + 8, dst + 8);
+    } else if constexpr (NV % 4 == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         const float4 t = *reinterpret_cast<const float4*>(src + i);
@@ -153,7 +197,10 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
     }
   };
   auto store_f32 = [&](float* dst, const float* src) {
-    if constexpr (NV % 4 == 0) {
+    if constexpr (NV == 16) {
+      st256(dst, src);
+      st256(dst + 8, src + 8);
+    } else if constexpr (NV % 4 == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
     } else {
@@ -168,7 +215,10 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
       __align__(16) __half l[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) split_f32(val[i], h[i], l[i]);
-      if constexpr (NV == 8) {
+      if constexpr (NV == 16) {
+        st256_b32(dhi + off, reinterpret_cast<const uint32_t*>(h));
+        st256_b32(dlo + off, reinterpret_cast<const uint32_t*>(l));
+      } else if constexpr (NV == 8) {
         *reinterpret_cast<uint4*>(dhi + off) = *reinterpret_cast<const uint4*>(h);
         *reinterpret_cast<uint4*>(dlo + off) = *reinterpret_cast<const uint4*>(l);
       } else if constexpr (NV == 4) {
@@ -243,7 +293,10 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
         y[i] = (p.div != 0.f) ? y[i] / p.div : p.scale * y[i];
       }
       float* dst = p.f0 + (size_t)pix * p.cout + c;
-      if (full && (p.cout & 3) == 0 && NV % 4 == 0) {
+      if constexpr (NV == 16) {
+        st256(dst, y);
+        st256(dst + 8, y + 8);
+      } else if (full && (p.cout & 3) == 0 && NV % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
       } else {

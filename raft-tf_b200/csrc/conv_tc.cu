@@ -48,13 +48,6 @@ struct TcCfg {
   static constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1 column groups of epilogue warps
 };
 
-struct TileGeom {
-  int bw_log2, bh_log2;  // box = 2^bh x 2^bw pixels, product 128
-  int tiles_x, tiles_y;  // per image
-  int n_tiles;           // cout tiles
-  int m_tiles;           // B * tiles_x * tiles_y pixel tiles
-  int total_tiles;       // work items: m_tiles * n_tiles, or ceil(m_tiles/2) * n_tiles PAIRS in cluster mode
-};
 
 // PAIR = true: CTAs are launched as clusters of two that work on two pixel tiles of the SAME cout tile; CTA 0 fetches
 // B_hi, CTA 1 fetches B_lo, each with TMA multicast into both CTAs' shared memory, so every SM issues only half of
@@ -75,6 +68,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  const bool wide = epilogue_wide_ok(p);
   if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   const int chunks = conv_chunks(p);
   const int taps = p.kh * p.kw;
@@ -213,8 +207,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
           if (valid) {
-            epilogue_store<8>(p, pix, n0 + c, v);
-            epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+            if (wide) {
+              epilogue_store<16>(p, pix, n0 + c, v);
+            } else {
+              epilogue_store<8>(p, pix, n0 + c, v);
+              epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+            }
           }
         }
         // this warp no longer needs the accumulator buffer: hand it back to the MMA warp
@@ -398,6 +396,38 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
 
 int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled);
 int launch_conv_tc2(const ConvParams& p, cudaStream_t s, int bn, int bw_log2, int bh_log2, int tiles_x, int tiles_y, bool* handled);
+
+// Geometry, tile width and tensor maps of one conv for the fused update-step kernel (update_fused.cu).
+int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
+  RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
+             "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
+  TileGeom g = choose_geom(p.h, p.w);
+  g.m_tiles = p.B * g.tiles_x * g.tiles_y;
+  const int bn = choose_block_n(p.cout, g.m_tiles);
+  g.n_tiles = (p.cout + bn - 1) / bn;
+  g.total_tiles = g.m_tiles * g.n_tiles;
+  job->p = p;
+  job->g = g;
+  job->block_n = bn;
+  {
+    uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
+    uint64_t str[3] = {(uint64_t)p.in_stride * 2, (uint64_t)p.in_stride * 2 * p.w, (uint64_t)p.in_stride * 2 * p.w * p.h};
+    uint32_t box[4] = {(uint32_t)kChunkK, 1u << g.bw_log2, 1u << g.bh_log2, 1};
+    int rc;
+    if ((rc = cached_tmap(&job->m[0], p.in_hi, 4, dims, str, box))) return rc;
+    if ((rc = cached_tmap(&job->m[1], p.in_lo, 4, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t ktot = (uint64_t)p.kh * p.kw * p.cin_pad;
+    uint64_t dims[3] = {ktot, (uint64_t)p.cout_pad, (uint64_t)(p.w_per_batch ? p.B : 1)};
+    uint64_t str[2] = {ktot * 2, ktot * 2 * p.cout_pad};
+    uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)bn, 1};
+    int rc;
+    if ((rc = cached_tmap(&job->m[2], p.w_hi, 3, dims, str, box))) return rc;
+    if ((rc = cached_tmap(&job->m[3], p.w_lo, 3, dims, str, box))) return rc;
+  }
+  return RB_OK;
+}
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   if (p.kh * p.kw > 1) {  // multi-tap convs: halo-tile kernel (each input pixel is fetched once per tap ROW, not per tap)

@@ -163,6 +163,36 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 
 }  // namespace tc
 
+struct TileGeom {
+  int bw_log2, bh_log2;  // box = 2^bh x 2^bw pixels, product 128
+  int tiles_x, tiles_y;  // per image
+  int n_tiles;           // cout tiles
+  int m_tiles;           // B * tiles_x * tiles_y pixel tiles
+  int total_tiles;       // work items: m_tiles * n_tiles, or ceil(m_tiles/2) * n_tiles PAIRS in cluster mode
+};
+
+// One conv of the fused update-step kernel (update_fused.cu)
+struct FusedJob {
+  CUtensorMap m[4];  // A_hi, A_lo, B_hi, B_lo
+  ConvParams p;
+  TileGeom g;
+  int block_n;
+  int wait_prev;   // 1: every earlier job of the list must be complete (grid barrier) before this job's loads
+  int cta_offset;  // tile t runs on CTA (t + cta_offset) % gridDim.x: independent jobs spread over different SMs
+  int pad_;
+};
+int conv_tc_prepare(const ConvParams& p, FusedJob* job);
+constexpr int kMaxFusedJobs = 12;
+struct FusedJobs {
+  FusedJob job[kMaxFusedJobs];
+  int n;
+  unsigned int* counters;  // [kMaxFusedJobs], zeroed before every launch
+  long long* dbg;          // tools/fused_times.py: 8 globaltimer stamps per (job, CTA), 4096 CTAs per job
+  int whatif;              // timing experiments only (RAFT_B200_WHATIF bitmask, results are WRONG): 1 no A_lo*B_hi MMA,
+                           // 2 no A_lo load, 4 no B loads, 8 no A_hi load, 16 no MMAs at all, 32 no epilogue stores
+};
+int launch_fused_jobs(const FusedJobs& jobs, cudaStream_t s);
+
 // per-thread cache of encoded tensor maps (conv_tc.cu)
 int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                 const uint32_t* box, int kind = tc::TMAP_F16_SW128);

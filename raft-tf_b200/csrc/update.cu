@@ -17,7 +17,7 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rb {
 
@@ -116,6 +116,7 @@ struct Workspace {
   float* H;
   float* Z;
   float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
+  unsigned int* counters;  // grid-barrier counters of the fused update-step kernel (update_fused.cu)
   size_t total;
 };
 
@@ -148,6 +149,8 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
       off += align_up(npix * (size_t)((i & 1) ? v.hidden : 2 * v.hidden) * sizeof(float), 1024);
     }
   }
+  W.counters = reinterpret_cast<unsigned int*>(b + off);
+  off += 1024;
   W.total = off;
   return W;
 }
@@ -311,8 +314,26 @@ static void hoist_inp(const Variant& v, const Workspace& W, int idx, ConvParams&
 // step record 8 timestamps per CTA for each of its convs, in launch order, 4096 CTAs per conv.
 static thread_local long long* g_dbg = nullptr;
 static thread_local int g_dbg_idx = 0;
+// Fused mode (RAFT_B200_FUSED=1): the convs of one update step are recorded into a job list and run as ONE
+// persistent kernel with grid barriers between dependent convs (update_fused.cu).
+static thread_local FusedJobs* g_rec = nullptr;
+static thread_local int g_rec_wait = 1, g_rec_offset = 0;
+static inline bool fused_mode() {
+  static const bool on = getenv("RAFT_B200_FUSED") != nullptr;
+  return on && math_mode() == RB_MATH_TC;
+}
 static int launch_conv_dbg(ConvParams& p, cudaStream_t s) {
   static const int early = getenv("RAFT_B200_PDL_EARLY") ? 1 : 0;
+  if (g_rec) {
+    RB_REQUIRE(g_rec->n < kMaxFusedJobs, RB_ERR_UNSUPPORTED, "fused update: too many convs");
+    FusedJob& jb = g_rec->job[g_rec->n];
+    int rc = conv_tc_prepare(p, &jb);
+    if (rc) return rc;
+    jb.wait_prev = g_rec_wait;
+    jb.cta_offset = g_rec_offset;
+    g_rec->n++;
+    return RB_OK;
+  }
   p.pdl_early = early;
   if (g_dbg) p.dbg = g_dbg + (size_t)(g_dbg_idx++) * 4096 * 8;
   return launch_conv(p, s);
@@ -357,6 +378,15 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   const int foff = xoff + v.mo_out;       // channel offset of the raw flow
   int rc;
   g_dbg_idx = 0;
+  FusedJobs jobs;
+  const bool fused = fused_mode();
+  if (fused) {
+    static const int whatif = getenv("RAFT_B200_WHATIF") ? atoi(getenv("RAFT_B200_WHATIF")) : 0;
+    jobs.n = 0; jobs.counters = W.counters; jobs.whatif = whatif; jobs.dbg = g_dbg; g_rec_wait = 1; g_rec_offset = 0;
+  }
+  struct RecGuard {  // recording never outlives this call, whatever the exit path
+    ~RecGuard() { g_rec = nullptr; }
+  } rec_guard;
   // ---- motion encoder (model_utils.py:110-129) ----
   SideStream* ss;
   if ((rc = side_stream(&ss))) return rc;
@@ -370,19 +400,39 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     if (v.small) flow_conv7_kernel<64><<<grid, 64, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
     else flow_conv7_kernel<128><<<grid, 128, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
     RB_CHECK_LAUNCH("flow_conv7_kernel");
-    ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
-    set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
-    if ((rc = launch_conv_dbg(p, ss->stream))) return rc;
+    if (!fused) {
+      ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
+      set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
+      if ((rc = launch_conv_dbg(p, ss->stream))) return rc;
+    }
     RB_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
   }
   // correlation branch (main stream): [lookup ->] convc1 [-> convc2]
   if (pyramid) {
     if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s))) return rc;
   }
+  if (fused) {
+    // both branches (flow_conv7 on the side stream, the lookup here) end before the fused kernel starts; its first two
+    // jobs (convc1, convf2) are independent of each other and are spread over different CTAs
+    RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+    g_rec = &jobs;
+    g_rec_wait = 0;
+  }
+  auto record_convf2 = [&]() -> int {
+    if (!fused) return RB_OK;
+    ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
+    set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
+    g_rec_offset = jobs.job[0].g.total_tiles;
+    int r = launch_conv_dbg(p, s);
+    g_rec_offset = 0;
+    g_rec_wait = 1;
+    return r;
+  };
   if (!v.small) {
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
     set_act(p, ACT_RELU, W.c1, v.c1, 0);
     if ((rc = launch_conv_dbg(p, s))) return rc;
+    if ((rc = record_convf2())) return rc;
     p = base_params(v, L, blob, P_CONVC2, W.c1, v.c1, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
     if ((rc = launch_conv_dbg(p, s))) return rc;
@@ -390,8 +440,9 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
     if ((rc = launch_conv_dbg(p, s))) return rc;
+    if ((rc = record_convf2())) return rc;
   }
-  RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+  if (!fused) RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   {
     ConvParams p = base_params(v, L, blob, P_MOTION, W.cf, v.cf, 0, B, h, w);
     set_act(p, ACT_RELU, W.hx, v.hx, xoff);
@@ -431,6 +482,10 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     p = base_params(v, L, blob, P_MASK2, W.fh, v.fh, 0, B, h, w);
     p.epi = EPI_F32; p.f0 = mask_out; p.scale = 0.25f;
     if ((rc = launch_conv_dbg(p, s))) return rc;
+  }
+  if (fused) {
+    g_rec = nullptr;
+    if ((rc = launch_fused_jobs(jobs, s))) return rc;
   }
   return RB_OK;
 }
