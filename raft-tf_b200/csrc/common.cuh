@@ -85,7 +85,8 @@ struct ConvParams {
   // (The iteration-invariant `inp` slice of the GRU inputs is convolved once per pair and skipped afterwards.)
   int ck_begin, ck_count, ck_skip_at, ck_skip;
   const float* addend;  // optional fp32 [pixel][cout] added to the accumulator before bias/activation
-  int pdl_early;        // 1: trigger dependents at kernel start instead of at epilogue start (tuning knob)
+  int pdl_early;
+  int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue        // 1: trigger dependents at kernel start instead of at epilogue start (tuning knob)
   long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py
   // packed weights [cout_pad][kh*kw][cin_pad] (K-major) as split planes + fp32 bias
   const __half* w_hi;
@@ -112,9 +113,19 @@ struct ConvParams {
 // Gate non-linearities on the SFU: exp via ex2.approx (abs. error of the gate < 3e-7 for |x| < 16, i.e.
 // below the 2^-22 operand truncation of the split GEMM that feeds them), reciprocal via rcp.approx.
 // r01 profile: with libm expf/tanhf + IEEE division the GRU epilogues took as long as their MMA loops.
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) {  // 1 - 2/(1+e^{2x}); exact limits at +-inf
-  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+  return fmaf(-2.0f, rcp_fast(1.0f + ex2_fast(2.8853900817779268f * x)), 1.0f);
 }
 
 // 256-bit global accesses (sm_100: LDG.256 / STG.256).  The tensor-core epilogues have one pixel per lane, so every lane
@@ -140,7 +151,9 @@ __device__ __forceinline__ void st256_b32(void* dst, const uint32_t* v) {
 }
 // All destinations / operands of the conv are 32-byte aligned at 16-channel granularity (uniform per launch).
 __device__ __forceinline__ bool epilogue_wide_ok(const ConvParams& p) {
-  bool ok = (p.cout & 15) == 0;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  bool ok = (p.cout & 15) == 0 && al(p.bias) && al(p.addend) && al(p.d0_hi) && al(p.d0_lo) && al(p.d1_hi) && al(p.d1_lo) &&
+            al(p.f0) && al(p.f1);
   if (p.epi == EPI_ACT) {
     ok = ok && ((p.d0_stride | p.d0_choff) & 15) == 0;
     if (p.d1_hi) ok = ok && ((p.d1_stride | p.d1_choff) & 15) == 0;
@@ -163,13 +176,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
   const bool full = (c + NV <= p.cout);
   if (p.addend) {
     const float* ad = p.addend + (size_t)pix * p.cout + c;
-    if constexpr (NV == 16) {  // wide path: the caller checked epilogue_wide_ok()
-      float t[16];
-      ld256_nc(ad, t);
-      ld256_nc(ad + 8, t + 8);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) y[i] += t[i];
-    } else if (full && NV % 4 == 0 && (p.cout & 3) == 0) {
+    if (full && NV % 4 == 0 && (p.cout & 3) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(ad + i));
@@ -182,10 +189,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
   }
 
   auto load_f32 = [&](const float* src, float* dst) {  // NV consecutive floats, 4*NV-byte aligned
-    if constexpr (NV == 16) {
-      ld256(src, dst);
-      ld256(src + 8, dst + 8);
-    } else if constexpr (NV % 4 == 0) {
+    if constexpr (NV % 4 == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         const float4 t = *reinterpret_cast<const float4*>(src + i);
@@ -197,10 +201,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
     }
   };
   auto store_f32 = [&](float* dst, const float* src) {
-    if constexpr (NV == 16) {
-      st256(dst, src);
-      st256(dst + 8, src + 8);
-    } else if constexpr (NV % 4 == 0) {
+    if constexpr (NV % 4 == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
     } else {
@@ -215,10 +216,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
       __align__(16) __half l[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) split_f32(val[i], h[i], l[i]);
-      if constexpr (NV == 16) {
-        st256_b32(dhi + off, reinterpret_cast<const uint32_t*>(h));
-        st256_b32(dlo + off, reinterpret_cast<const uint32_t*>(l));
-      } else if constexpr (NV == 8) {
+      if constexpr (NV == 8) {
         *reinterpret_cast<uint4*>(dhi + off) = *reinterpret_cast<const uint4*>(h);
         *reinterpret_cast<uint4*>(dlo + off) = *reinterpret_cast<const uint4*>(l);
       } else if constexpr (NV == 4) {
@@ -293,16 +291,124 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
         y[i] = (p.div != 0.f) ? y[i] / p.div : p.scale * y[i];
       }
       float* dst = p.f0 + (size_t)pix * p.cout + c;
-      if constexpr (NV == 16) {
-        st256(dst, y);
-        st256(dst + 8, y + 8);
-      } else if (full && (p.cout & 3) == 0 && NV % 4 == 0) {
+      if (full && (p.cout & 3) == 0 && NV % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
       } else {
         for (int i = 0; i < NV; ++i)
           if (c + i < p.cout) dst[i] = y[i];
       }
+    } break;
+  }
+}
+
+// ---- lean 16-channel epilogue (tensor-core kernels, epilogue_wide_ok() launches) ----------------------------------
+// Same arithmetic as epilogue_store<NV>, element for element; 256-bit global accesses, no per-element bounds logic.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void store_split16(const ConvParams& p, __half* dhi, __half* dlo, size_t off, const float* y) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2(y[2 * i], y[2 * i + 1], h[i], l[i]);
+  if (!(p.whatif & 64)) {
+    st256_b32(dhi + off, h);
+    st256_b32(dlo + off, l);
+  } else if (h[0] == 0x12345678u) {  // timing experiment: keep the math alive
+    dhi[off] = __float2half(1.f);
+  }
+}
+__device__ __forceinline__ void load16(const ConvParams& p, const float* src, float* d) {
+  if (!(p.whatif & 128)) {
+    ld256(src, d);
+    ld256(src + 8, d + 8);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = 0.5f;
+  }
+}
+__device__ __forceinline__ void store16(const ConvParams& p, float* dst, const float* v) {
+  if (!(p.whatif & 64)) {
+    st256(dst, v);
+    st256(dst + 8, v + 8);
+  } else if (v[0] == 12345.678f) {
+    dst[0] = 1.f;
+  }
+}
+__device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, int c, float* y) {
+  if (p.bias) {
+    float t[16];
+    ld256_nc(p.bias + c, t);
+    ld256_nc(p.bias + c + 8, t + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] += t[i];
+  }
+  if (p.addend) {
+    float t[16];
+    const float* ad = p.addend + (size_t)pix * p.cout + c;
+    if (!(p.whatif & 128)) {
+      ld256_nc(ad, t);
+      ld256_nc(ad + 8, t + 8);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] = 0.25f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] += t[i];
+  }
+  switch (p.epi) {
+    case EPI_ACT: {
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      store_split16(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + c, y);
+      if (p.d1_hi) store_split16(p, p.d1_hi, p.d1_lo, (size_t)pix * p.d1_stride + p.d1_choff + c, y);
+    } break;
+    case EPI_ZR: {
+      if (c < p.hidden) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = sigmoid_f(y[i]);
+        store16(p, p.f0 + (size_t)pix * p.hidden + c, y);
+      } else {
+        const int ch = c - p.hidden;
+        float hprev[16];
+        load16(p, p.f1 + (size_t)pix * p.hidden + ch, hprev);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = sigmoid_f(y[i]) * hprev[i];
+        store_split16(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + ch, y);
+      }
+    } break;
+    case EPI_Q: {
+      float z[16], hprev[16];
+      float* hp = p.f1 + (size_t)pix * p.hidden + c;
+      load16(p, p.f0 + (size_t)pix * p.hidden + c, z);
+      load16(p, hp, hprev);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float q = tanh_f(y[i]);
+        y[i] = (1.0f - z[i]) * hprev[i] + z[i] * q;  // model_utils.py:147,155,168
+      }
+      store16(p, hp, y);
+      store_split16(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + c, y);
+    } break;
+    default: {  // EPI_F32
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      if (p.div != 0.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = y[i] / p.div;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = p.scale * y[i];
+      }
+      store16(p, p.f0 + (size_t)pix * p.cout + c, y);
     } break;
   }
 }

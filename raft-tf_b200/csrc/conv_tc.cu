@@ -188,7 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const bool valid = (py < p.h) && (px < p.w) && (mt < g.m_tiles);
         const int pix = (b * p.h + py) * p.w + px;
         const int ab = li & 1;
-        mbar_wait(&tmem_full_bar[ab], (li >> 1) & 1);
+        mbar_wait_warp(&tmem_full_bar[ab], (li >> 1) & 1);
         tc_fence_after();
         if (li == 0) {
           asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -208,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
           if (valid) {
             if (wide) {
-              epilogue_store<16>(p, pix, n0 + c, v);
+              epilogue_wide16(p, pix, n0 + c, v);
             } else {
               epilogue_store<8>(p, pix, n0 + c, v);
               epilogue_store<8>(p, pix, n0 + c + 8, v + 8);

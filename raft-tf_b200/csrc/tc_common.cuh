@@ -49,6 +49,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Whole-warp wait with ONE polling lane and a short back-off: 16 epilogue warps spinning with all lanes on the
+// accumulator barrier for the length of an MMA loop compete with the producer / MMA threads for the barrier unit.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(32);
+      if ((++spins & 0x3FF) == 0) {
+        long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) {
+          printf("raft_b200: mbarrier wait timed out (block %d warp %d parity %u)\n", blockIdx.x, threadIdx.x >> 5, parity);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

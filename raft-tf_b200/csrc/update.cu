@@ -327,6 +327,7 @@ static int launch_conv_dbg(ConvParams& p, cudaStream_t s) {
   if (g_rec) {
     RB_REQUIRE(g_rec->n < kMaxFusedJobs, RB_ERR_UNSUPPORTED, "fused update: too many convs");
     FusedJob& jb = g_rec->job[g_rec->n];
+    p.whatif = g_rec->whatif;
     int rc = conv_tc_prepare(p, &jb);
     if (rc) return rc;
     jb.wait_prev = g_rec_wait;

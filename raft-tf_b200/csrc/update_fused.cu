@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
         const bool valid = (py < p.h) && (px < p.w);
         const int pix = (b * p.h + py) * p.w + px;
         const int ab = li & 1;
-        mbar_wait(&tmem_full_bar[ab], (li >> 1) & 1);
+        mbar_wait_warp(&tmem_full_bar[ab], (li >> 1) & 1);
         tc_fence_after();
         if (dbg && first) dbg[4] = gtime_ns();
         if (first) {
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
             if (valid && !(J.whatif & 32)) {
               if (wide) {
-                epilogue_store<16>(p, pix, n0 + c, v);
+                epilogue_wide16(p, pix, n0 + c, v);
               } else {
                 epilogue_store<8>(p, pix, n0 + c, v);
                 epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
