@@ -87,7 +87,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything of ours can reach them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // warp-wide OR of identical values: lands in a UNIFORM register, so that ptxas does not wrap every tcgen05.mma of the
+  // single issuing lane in an elect / R2UR.BROADCAST "waterfall" loop (that was ~50 cycles per MMA, 8 MMAs per k-iteration)
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
   const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
   const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -97,9 +99,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (dbg && threadIdx.x == 0) dbg[2] = gtime_ns();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-      int git = 0;  // ring position, continues across tiles
+      int s = 0;          // ring slot and its phase; both continue across tiles.  No integer division in this loop:
+      uint32_t phase = 0;  // the k-iteration -> (chunk, kx, ky) mapping is advanced incrementally.
       for (int tile = first; tile < g.total_tiles; tile += stride) {
         const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
         const int mt = PAIR ? 2 * mq + rank : mq;  // a trailing odd tile gets a dummy partner: b >= B, TMA zero-fills
@@ -107,18 +110,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
         const int wb = p.w_per_batch ? min(b, p.B - 1) : 0;
-        for (int it = 0; it < kiters; ++it, ++git) {
-          const int s = git % STAGES;
-          const uint32_t phase = (git / STAGES) & 1;
+        // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
+        // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
+        // per-sample runs bit for bit.
+        int cki = 0, kx = 0, ky = 0, ck = conv_chunk(p, 0);
+        for (int it = 0; it < kiters; ++it) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* st = smem + s * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
-          // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
-          // per-sample runs bit for bit.
-          const int cki = it / taps, tt = it - cki * taps;
-          const int ck = conv_chunk(p, cki);
-          const int kx = tt / p.kh, ky = tt - kx * p.kh;
           const int t = ky * p.kw + kx;
           const int dy = ky - ph, dx = kx - pw;
           const int c0 = p.in_choff + ck * kChunkK;
@@ -132,26 +131,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
             tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
           }
+          if (++ky == p.kh) {
+            ky = 0;
+            if (++kx == p.kw) { kx = 0; ck = conv_chunk(p, ++cki); }
+          }
+          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
       constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
-      int git = 0, li = 0;
+      int s = 0, li = 0;
+      uint32_t phase = 0;
       for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int ab = li & 1;
         mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + ab * Cfg::kAccCols;
-        for (int it = 0; it < kiters; ++it, ++git) {
-          const int s = git % STAGES;
-          const uint32_t phase = (git / STAGES) & 1;
+        for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
-          if (dbg && git == 0) dbg[3] = gtime_ns();
+          if (dbg && li == 0 && it == 0) dbg[3] = gtime_ns();
           const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
           const uint64_t a_hi = umma_desc_sw128(st);
           const uint64_t a_lo = umma_desc_sw128(st + kATileBytes);
@@ -164,6 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           if (PAIR) umma_commit_mc(&empty_bar[s], (uint16_t)3);  // both producers write into this stage of both CTAs
           else umma_commit(&empty_bar[s]);                      // frees the smem stage when these MMAs retire
+          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[ab]);
         if (dbg && li == 0) dbg[4] = gtime_ns();

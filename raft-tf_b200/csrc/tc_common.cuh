@@ -49,6 +49,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows that exactly one thread runs the guarded region, so the
+// uniform-datapath instructions in it (UTCHMMA, UTMALDG, UTCBAR) are emitted directly instead of inside an
+// elect / branch "waterfall" loop each (profiles/r01_notes.md: that loop was the k-iteration floor of the MMA warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Whole-warp wait with ONE polling lane and a short back-off: 16 epilogue warps spinning with all lanes on the
 // accumulator barrier for the length of an MMA loop compete with the producer / MMA threads for the barrier unit.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
@@ -208,6 +219,7 @@ struct FusedJobs {
   FusedJob job[kMaxFusedJobs];
   int n;
   unsigned int* counters;  // [kMaxFusedJobs], zeroed before every launch
+  int stages;              // smem ring depth (<= 3)
   long long* dbg;          // tools/fused_times.py: 8 globaltimer stamps per (job, CTA), 4096 CTAs per job
   int whatif;              // timing experiments only (RAFT_B200_WHATIF bitmask, results are WRONG): 1 no A_lo*B_hi MMA,
                            // 2 no A_lo load, 4 no B loads, 8 no A_hi load, 16 no MMAs at all, 32 no epilogue stores

@@ -383,7 +383,9 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   const bool fused = fused_mode();
   if (fused) {
     static const int whatif = getenv("RAFT_B200_WHATIF") ? atoi(getenv("RAFT_B200_WHATIF")) : 0;
-    jobs.n = 0; jobs.counters = W.counters; jobs.whatif = whatif; jobs.dbg = g_dbg; g_rec_wait = 1; g_rec_offset = 0;
+    jobs.n = 0; jobs.counters = W.counters; jobs.whatif = whatif; jobs.dbg = g_dbg;
+    static const int st = getenv("RAFT_B200_FUSED_STAGES") ? atoi(getenv("RAFT_B200_FUSED_STAGES")) : 3;
+    jobs.stages = st < 1 ? 1 : (st > 3 ? 3 : st); g_rec_wait = 1; g_rec_offset = 0;
   }
   struct RecGuard {  // recording never outlives this call, whatever the exit path
     ~RecGuard() { g_rec = nullptr; }

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (int)gridDim.x;
+  const int NS = J.stages;  // <= kFStages (tuning knob RAFT_B200_FUSED_STAGES)
 
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < J.n; ++j)
@@ -59,11 +60,14 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // warp-wide OR of identical values: lands in a UNIFORM register, so that ptxas does not wrap every tcgen05.mma of the
+  // single issuing lane in an elect / R2UR.BROADCAST "waterfall" loop (that was ~50 cycles per MMA, 8 MMAs per k-iteration)
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int git = 0;
+    if (elect_one()) {
+      int rs = 0;          // ring slot and its phase (continue across tiles and jobs; no integer division per k-iteration)
+      uint32_t rph = 0;
       for (int j = 0; j < J.n; ++j) {
         const FusedJob& jb = J.job[j];
         const ConvParams& p = jb.p;
@@ -84,28 +88,44 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
           const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
           const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * bn;
           const int wb = p.w_per_batch ? b : 0;
-          auto kcoords = [&](int it, int& c0, int& dx, int& dy, int& kcol) {
-            const int cki = it / taps, tt = it - cki * taps;
-            const int ck = conv_chunk(p, cki);
-            const int kx = tt / p.kh, ky = tt - kx * p.kh;
-            c0 = p.in_choff + ck * 64; dx = kx - pw; dy = ky - ph;
-            kcol = (ky * p.kw + kx) * p.cin_pad + ck * 64;
+          // k-iteration -> (channel chunk, kx, ky): chunk outermost, then kx, then ky (the order of conv_tc.cu)
+          struct KIter {
+            int cki, kx, ky, ck;
           };
+          auto k_next = [&](KIter& k) {
+            if (++k.ky == p.kh) {
+              k.ky = 0;
+              if (++k.kx == p.kw) { k.kx = 0; k.ck = conv_chunk(p, ++k.cki); }
+            }
+          };
+          auto load_a = [&](const KIter& k, int s) {
+            uint8_t* st = smem + s * kFStageStride;
+            const int c0 = p.in_choff + k.ck * 64;
+            if (!(wi & 8)) tma_load_4d(&jb.m[0], &full_bar[s], st, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
+            if (!(wi & 2)) tma_load_4d(&jb.m[1], &full_bar[s], st + kFATile, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
+          };
+          auto load_b = [&](const KIter& k, int s) {
+            uint8_t* st = smem + s * kFStageStride;
+            const int kcol = (k.ky * p.kw + k.kx) * p.cin_pad + k.ck * 64;
+            if (!(wi & 4)) {
+              tma_load_3d(&jb.m[2], &full_bar[s], st + 2 * kFATile, kcol, n0, wb);
+              tma_load_3d(&jb.m[3], &full_bar[s], st + 2 * kFATile + btile, kcol, n0, wb);
+            }
+          };
+          KIter k = {0, 0, 0, conv_chunk(p, 0)};
           int it0 = 0;
           if (must_wait) {
             // weights first (they do not depend on earlier jobs), for as many stages as the ring has ...
-            const int pre = kiters < kFStages ? kiters : kFStages;
+            const int pre = kiters < NS ? kiters : NS;
+            KIter kb = k;
+            int s = rs;
+            uint32_t sph = rph;
             for (int it = 0; it < pre; ++it) {
-              const int s = (git + it) % kFStages;
-              mbar_wait(&empty_bar[s], (((git + it) / kFStages) & 1) ^ 1);
-              uint8_t* st = smem + s * kFStageStride;
+              mbar_wait(&empty_bar[s], sph ^ 1);
               mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-              int c0, dx, dy, kcol;
-              kcoords(it, c0, dx, dy, kcol);
-              if (!(wi & 4)) {
-                tma_load_3d(&jb.m[2], &full_bar[s], st + 2 * kFATile, kcol, n0, wb);
-                tma_load_3d(&jb.m[3], &full_bar[s], st + 2 * kFATile + btile, kcol, n0, wb);
-              }
+              load_b(kb, s);
+              k_next(kb);
+              if (++s == NS) { s = 0; sph ^= 1; }
             }
             // ... then the grid barrier: every epilogue warp of every CTA has finished the previous jobs
             const unsigned target = 16u * (unsigned)G;
@@ -121,37 +141,28 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
             fence_proxy_async();
             if (dbg) dbg[1] = gtime_ns();
             for (int it = 0; it < pre; ++it) {
-              const int s = (git + it) % kFStages;
-              uint8_t* st = smem + s * kFStageStride;
-              int c0, dx, dy, kcol;
-              kcoords(it, c0, dx, dy, kcol);
-              if (!(wi & 8)) tma_load_4d(&jb.m[0], &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
-              if (!(wi & 2)) tma_load_4d(&jb.m[1], &full_bar[s], st + kFATile, c0, x0 + dx, y0 + dy, b);
+              load_a(k, rs);
+              k_next(k);
+              if (++rs == NS) { rs = 0; rph ^= 1; }
             }
             it0 = pre;
             must_wait = false;
           }
           for (int it = it0; it < kiters; ++it) {
-            const int s = (git + it) % kFStages;
-            mbar_wait(&empty_bar[s], (((git + it) / kFStages) & 1) ^ 1);
-            uint8_t* st = smem + s * kFStageStride;
-            mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-            int c0, dx, dy, kcol;
-            kcoords(it, c0, dx, dy, kcol);
-            if (!(wi & 8)) tma_load_4d(&jb.m[0], &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
-            if (!(wi & 2)) tma_load_4d(&jb.m[1], &full_bar[s], st + kFATile, c0, x0 + dx, y0 + dy, b);
-            if (!(wi & 4)) {
-              tma_load_3d(&jb.m[2], &full_bar[s], st + 2 * kFATile, kcol, n0, wb);
-              tma_load_3d(&jb.m[3], &full_bar[s], st + 2 * kFATile + btile, kcol, n0, wb);
-            }
+            mbar_wait(&empty_bar[rs], rph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[rs], stage_tx);
+            load_a(k, rs);
+            load_b(k, rs);
+            k_next(k);
+            if (++rs == NS) { rs = 0; rph ^= 1; }
           }
-          git += kiters;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int git = 0, li = 0;
+    if (elect_one()) {
+      int rs = 0, li = 0;
+      uint32_t rph = 0;
       for (int j = 0; j < J.n; ++j) {
         const FusedJob& jb = J.job[j];
         const ConvParams& p = jb.p;
@@ -166,9 +177,9 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
           mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t acc = tmem_base + ab * 256;
-          for (int it = 0; it < kiters; ++it, ++git) {
-            const int s = git % kFStages;
-            mbar_wait(&full_bar[s], (git / kFStages) & 1);
+          for (int it = 0; it < kiters; ++it) {
+            const int s = rs;
+            mbar_wait(&full_bar[s], rph);
             tc_fence_after();
             if (dbg && first_tile && it == 0) dbg[2] = gtime_ns();
             const uint32_t st = smem_u32(smem + s * kFStageStride);
@@ -181,6 +192,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
               if (!(J.whatif & 17)) umma_f16(acc + bn, a_lo + koff, b_all + koff, idesc_n, 1u);
             }
             umma_commit(&empty_bar[s]);
+            if (++rs == NS) { rs = 0; rph ^= 1; }
           }
           umma_commit(&tmem_full_bar[ab]);
           if (dbg && first_tile) dbg[3] = gtime_ns();
