@@ -89,77 +89,85 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);  // uniform register (see conv_tc.cu)
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (dbg && threadIdx.x == 0) dbg[2] = gtime_ns();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
+      // no integer division inside the loops: (chunk, F-tap) groups and ring slots advance incrementally
       const int padF = (g.kF - 1) / 2, padS = (g.kS - 1) / 2;
       const uint32_t a_bytes = 2u * (uint32_t)g.halo_rows * 128u;
-      auto issue_a = [&](int grp) {
-        const int st = grp % kAStages;
-        const uint32_t phase = (grp / kAStages) & 1;
-        mbar_wait(&a_empty[st], phase ^ 1);
-        mbar_arrive_expect_tx(&a_full[st], a_bytes);
-        const int f = grp % g.kF, ck = conv_chunk(p, grp / g.kF);
-        uint8_t* dst = smemA + st * kAStageBytes;
+      int ast = 0;
+      uint32_t aph = 0;
+      auto issue_a = [&](int cki, int f) {
+        mbar_wait(&a_empty[ast], aph ^ 1);
+        mbar_arrive_expect_tx(&a_full[ast], a_bytes);
+        const int ck = conv_chunk(p, cki);
+        uint8_t* dst = smemA + ast * kAStageBytes;
         const int c0 = p.in_choff + ck * 64;
         // box origin: F coordinate shifted by the F-tap, S coordinate by -padS (halo covers all S-taps)
-        tma_load_4d(&tmA_hi, &a_full[st], dst, c0, f0 + f - padF, s0 - padS, b);
-        tma_load_4d(&tmA_lo, &a_full[st], dst + g.halo_rows * 128, c0, f0 + f - padF, s0 - padS, b);
+        tma_load_4d(&tmA_hi, &a_full[ast], dst, c0, f0 + f - padF, s0 - padS, b);
+        tma_load_4d(&tmA_lo, &a_full[ast], dst + g.halo_rows * 128, c0, f0 + f - padF, s0 - padS, b);
+        if (++ast == kAStages) { ast = 0; aph ^= 1; }
       };
       const int wb = p.w_per_batch ? b : 0;
-      int bi = 0;
-      issue_a(0);
-      for (int grp = 0; grp < groups; ++grp) {
-        const int f = grp % g.kF, ck = conv_chunk(p, grp / g.kF);
-        for (int s = 0; s < g.kS; ++s, ++bi) {
-          const int st = bi % NB;
-          const uint32_t phase = (bi / NB) & 1;
-          mbar_wait(&b_empty[st], phase ^ 1);
-          mbar_arrive_expect_tx(&b_full[st], Cfg::kBStageBytes);
-          // filter tap (ky,kx): the S-tap walks x for 1x5 convs, y otherwise
-          const int ky = g.s_is_x ? f : s, kx = g.s_is_x ? s : f;
-          const int kcol = (ky * p.kw + kx) * p.cin_pad + ck * 64;
-          uint8_t* dst = smemB + st * Cfg::kBStageBytes;
-          tma_load_3d(&tmB_hi, &b_full[st], dst, kcol, n0, wb);
-          tma_load_3d(&tmB_lo, &b_full[st], dst + BLOCK_N * 128, kcol, n0, wb);
+      int bst = 0;
+      uint32_t bph = 0;
+      issue_a(0, 0);
+      for (int cki = 0; cki < chunks; ++cki) {
+        const int ck = conv_chunk(p, cki);
+        for (int f = 0; f < g.kF; ++f) {
+          for (int s = 0; s < g.kS; ++s) {
+            mbar_wait(&b_empty[bst], bph ^ 1);
+            mbar_arrive_expect_tx(&b_full[bst], Cfg::kBStageBytes);
+            // filter tap (ky,kx): the S-tap walks x for 1x5 convs, y otherwise
+            const int ky = g.s_is_x ? f : s, kx = g.s_is_x ? s : f;
+            const int kcol = (ky * p.kw + kx) * p.cin_pad + ck * 64;
+            uint8_t* dst = smemB + bst * Cfg::kBStageBytes;
+            tma_load_3d(&tmB_hi, &b_full[bst], dst, kcol, n0, wb);
+            tma_load_3d(&tmB_lo, &b_full[bst], dst + BLOCK_N * 128, kcol, n0, wb);
+            if (++bst == NB) { bst = 0; bph ^= 1; }
+          }
+          if (f + 1 < g.kF) issue_a(cki, f + 1);
+          else if (cki + 1 < chunks) issue_a(cki + 1, 0);
         }
-        if (grp + 1 < groups) issue_a(grp + 1);
       }
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // every warp issues the PDL trigger once its part is done
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
       constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
-      int bi = 0;
+      int ast = 0, bst = 0;
+      uint32_t aph = 0, bph = 0;
+      bool first = true;
       for (int grp = 0; grp < groups; ++grp) {
-        const int ast = grp % kAStages;
-        mbar_wait(&a_full[ast], (grp / kAStages) & 1);
+        mbar_wait(&a_full[ast], aph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smemA + ast * kAStageBytes);
-        for (int s = 0; s < g.kS; ++s, ++bi) {
-          const int st = bi % NB;
-          mbar_wait(&b_full[st], (bi / NB) & 1);
+        for (int s = 0; s < g.kS; ++s) {
+          mbar_wait(&b_full[bst], bph);
           tc_fence_after();
-          if (dbg && bi == 0) dbg[3] = gtime_ns();
+          if (dbg && first) dbg[3] = gtime_ns();
           const uint32_t view = a_base + (uint32_t)(s * P) * 128u;  // shifted by s taps along S: multiple of 1024 B
           const uint64_t a_hi = umma_desc_sw128(view);
           const uint64_t a_lo = umma_desc_sw128(view + (uint32_t)g.halo_rows * 128u);
-          const uint64_t b_all = umma_desc_sw128(smem_u32(smemB + st * Cfg::kBStageBytes));
+          const uint64_t b_all = umma_desc_sw128(smem_u32(smemB + bst * Cfg::kBStageBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t koff = (uint64_t)(k * 2);
-            umma_f16(tmem_base, a_hi + koff, b_all + koff, idesc_2n, (bi | k) != 0);
+            umma_f16(tmem_base, a_hi + koff, b_all + koff, idesc_2n, (!first || k != 0) ? 1u : 0u);
             umma_f16(tmem_base + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
           }
-          umma_commit(&b_empty[st]);
+          first = false;
+          umma_commit(&b_empty[bst]);
+          if (++bst == NB) { bst = 0; bph ^= 1; }
         }
         umma_commit(&a_empty[ast]);
+        if (++ast == kAStages) { ast = 0; aph ^= 1; }
       }
       umma_commit(tmem_full_bar);
       if (dbg) dbg[4] = gtime_ns();
@@ -177,8 +185,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int pix = (b * p.h + py) * p.w + px;
     if (grp >= kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (grp < kGroups) {
-      mbar_wait(tmem_full_bar, 0);
+      mbar_wait_warp(tmem_full_bar, 0);
       tc_fence_after();
+      const bool wide = epilogue_wide_ok(p);
       // PDL trigger: only now (MMA loop done, epilogue starting) may the next kernel's CTAs be scheduled -- triggering
       // at kernel start let them take the SMs this kernel's own late CTAs were waiting for (phase_times.py).
       asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -196,8 +205,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
         if (valid) {
-          epilogue_store<8>(p, pix, n0 + c, v);
-          epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+          if (wide) {
+            epilogue_wide16(p, pix, n0 + c, v);
+          } else {
+            epilogue_store<8>(p, pix, n0 + c, v);
+            epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+          }
         }
       }
     }

@@ -76,12 +76,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);  // uniform register (see conv_tc.cu)
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-      int git = 0;
+      int s = 0;
+      uint32_t phase = 0;
       for (int tile = first; tile < g.total_pairs; tile += stride) {
         const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
         const int mt = 2 * mq + rank;
@@ -90,16 +91,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2;
         const int nrow0 = nt * BLOCK_N + rank * (BLOCK_N / 2);  // this CTA's half of the weight rows
         const int wb = p.w_per_batch ? min(b, p.B - 1) : 0;
-        for (int it = 0; it < kiters; ++it, ++git) {
-          const int s = git % STAGES;
-          const uint32_t phase = (git / STAGES) & 1;
+        int cki = 0, kx = 0, ky = 0, ck = conv_chunk(p, 0);
+        for (int it = 0; it < kiters; ++it) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* st = smem + s * Cfg::kStageBytes;
           const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);  // bytes of BOTH CTAs
-          const int cki = it / taps, tt = it - cki * taps;
-          const int ck = conv_chunk(p, cki);
-          const int kx = tt / p.kh, ky = tt - kx * p.kh;
           const int t = ky * p.kw + kx;
           const int c0 = p.in_choff + ck * 64;
           tma_load_4d_2sm(&tmA_hi, lead_full, st, c0, x0 + kx - pw, y0 + ky - ph, b);
@@ -108,21 +105,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tma_load_3d_2sm(&tmB_hi, lead_full, st + 2 * kA2Bytes, kcol, nrow0, wb);
           tma_load_3d_2sm(&tmB_lo, lead_full, st + 2 * kA2Bytes + Cfg::kBHalfBytes, kcol, nrow0, wb);
           if (!leader) mbar_arrive_remote(lead_full);
+          if (++ky == p.kh) {
+            ky = 0;
+            if (++kx == p.kw) { kx = 0; ck = conv_chunk(p, ++cki); }
+          }
+          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_f16_m256(BLOCK_N);
-      int git = 0, li = 0;
+      int s = 0, li = 0;
+      uint32_t phase = 0;
       for (int tile = first; tile < g.total_pairs; tile += stride, ++li) {
         const int ab = li & 1;
         mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + ab * Cfg::kAccCols;
-        for (int it = 0; it < kiters; ++it, ++git) {
-          const int s = git % STAGES;
-          mbar_wait(&full_bar[s], (git / STAGES) & 1);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[s], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
           const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kA2Bytes);
@@ -135,12 +137,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             umma_f16_2sm(acc + BLOCK_N, a_lo + koff, b_hi + koff, idesc, 1u);
           }
           umma_commit_2sm_mc(&empty_bar[s], (uint16_t)3);
+          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
         umma_commit_2sm_mc(&tmem_full_bar[ab], (uint16_t)3);
       }
     }
   } else {
     const int q = warp & 3, grp = (warp - 2) >> 2, r = q * 32 + lane;
+    const bool wide = epilogue_wide_ok(p);
     if (grp < Cfg::kGroups) {
       int li = 0;
       for (int tile = first; tile < g.total_pairs; tile += stride, ++li) {
@@ -168,8 +172,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
           if (valid) {
-            epilogue_store<8>(p, pix, n0 + c, v);
-            epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+            if (wide) {
+              epilogue_wide16(p, pix, n0 + c, v);
+            } else {
+              epilogue_store<8>(p, pix, n0 + c, v);
+              epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
+            }
           }
         }
         tc_fence_before();
