@@ -95,14 +95,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
-  if (dbg && threadIdx.x == 0) dbg[2] = gtime_ns();
+  // Programmatic dependent launch: this kernel may have been started while its predecessor is still running.  Everything
+  // up to here (barriers, TMEM, tensor-map prefetch) and the WEIGHT tiles of the first ring stages are independent of
+  // it; `griddepcontrol.wait` (no-op without the launch attribute) is executed by the producer before its first
+  // activation load and by every epilogue warp before its first global access.  The MMA warp touches no global memory.
 
   if (warp == 0) {
     if (elect_one()) {
       const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
       int s = 0;          // ring slot and its phase; both continue across tiles.  No integer division in this loop:
       uint32_t phase = 0;  // the k-iteration -> (chunk, kx, ky) mapping is advanced incrementally.
+      bool waited = false;
       for (int tile = first; tile < g.total_tiles; tile += stride) {
         const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
         const int mt = PAIR ? 2 * mq + rank : mq;  // a trailing odd tile gets a dummy partner: b >= B, TMA zero-fills
@@ -113,28 +116,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
         // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
         // per-sample runs bit for bit.
-        int cki = 0, kx = 0, ky = 0, ck = conv_chunk(p, 0);
-        for (int it = 0; it < kiters; ++it) {
-          mbar_wait(&empty_bar[s], phase ^ 1);
-          uint8_t* st = smem + s * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          const int t = ky * p.kw + kx;
-          const int dy = ky - ph, dx = kx - pw;
-          const int c0 = p.in_choff + ck * kChunkK;
-          tma_load_4d(&tmA_hi, &full_bar[s], st, c0, x0 + dx, y0 + dy, b);
-          tma_load_4d(&tmA_lo, &full_bar[s], st + kATileBytes, c0, x0 + dx, y0 + dy, b);
-          const int kcol = t * p.cin_pad + ck * kChunkK;
+        struct KIter {
+          int cki, kx, ky, ck;
+        };
+        auto k_next = [&](KIter& k) {
+          if (++k.ky == p.kh) {
+            k.ky = 0;
+            if (++k.kx == p.kw) { k.kx = 0; k.ck = conv_chunk(p, ++k.cki); }
+          }
+        };
+        auto load_a = [&](const KIter& k, int slot) {
+          uint8_t* st = smem + slot * Cfg::kStageBytes;
+          const int c0 = p.in_choff + k.ck * kChunkK;
+          tma_load_4d(&tmA_hi, &full_bar[slot], st, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
+          tma_load_4d(&tmA_lo, &full_bar[slot], st + kATileBytes, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
+        };
+        auto load_b = [&](const KIter& k, int slot) {
+          uint8_t* st = smem + slot * Cfg::kStageBytes;
+          const int kcol = (k.ky * p.kw + k.kx) * p.cin_pad + k.ck * kChunkK;
           if (PAIR) {  // half of the weight tile each, delivered to both CTAs
-            if (rank == 0) tma_load_3d_mc(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb, (uint16_t)3);
-            else tma_load_3d_mc(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb, (uint16_t)3);
+            if (rank == 0) tma_load_3d_mc(&tmB_hi, &full_bar[slot], st + 2 * kATileBytes, kcol, n0, wb, (uint16_t)3);
+            else tma_load_3d_mc(&tmB_lo, &full_bar[slot], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb, (uint16_t)3);
           } else {
-            tma_load_3d(&tmB_hi, &full_bar[s], st + 2 * kATileBytes, kcol, n0, wb);
-            tma_load_3d(&tmB_lo, &full_bar[s], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+            tma_load_3d(&tmB_hi, &full_bar[slot], st + 2 * kATileBytes, kcol, n0, wb);
+            tma_load_3d(&tmB_lo, &full_bar[slot], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
           }
-          if (++ky == p.kh) {
-            ky = 0;
-            if (++kx == p.kw) { kx = 0; ck = conv_chunk(p, ++cki); }
+        };
+        KIter k = {0, 0, 0, conv_chunk(p, 0)};
+        int it0 = 0;
+        if (!waited) {
+          // first tile of the kernel: weight tiles of the first ring stages, then wait for the predecessor kernel, then
+          // the activation tiles of the same stages (the ring is empty here: slots 0.., phase 0)
+          // (not when the B operand is itself an activation produced by an earlier kernel: corr build, w_per_batch)
+          const int pre = (PAIR || p.w_per_batch) ? 0 : (kiters < STAGES ? kiters : STAGES);
+          KIter kb = k;
+          for (int it = 0; it < pre; ++it) {
+            mbar_arrive_expect_tx(&full_bar[it], Cfg::kStageBytes);
+            load_b(kb, it);
+            k_next(kb);
           }
+          asm volatile("griddepcontrol.wait;" ::: "memory");
+          if (dbg) dbg[2] = gtime_ns();
+          for (int it = 0; it < pre; ++it) {
+            load_a(k, s);
+            k_next(k);
+            if (++s == STAGES) { s = 0; phase ^= 1; }
+          }
+          it0 = pre;
+          waited = true;
+        }
+        for (int it = it0; it < kiters; ++it) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          load_a(k, s);
+          load_b(k, s);
+          k_next(k);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
@@ -181,6 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int r = q * 32 + lane;  // tile row = pixel index inside the box
     if (grp >= Cfg::kGroups) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (grp < Cfg::kGroups) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // addend / z / h reads and all stores come after the predecessor
       int li = 0;
       for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
@@ -385,10 +422,9 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  // Programmatic dependent launch is OFF by default: measured on the update block (profiles/r01_notes.md) it hides
-  // the ~3.5 us launch gap but the dependents' CTAs then wait just as long for the grid-completion signal (early
-  // trigger: 222 us, trigger after the MMA loop: 220 us, no PDL: 217 us per step).  RAFT_B200_PDL=1 enables it.
-  static const int pdl = getenv("RAFT_B200_PDL") ? 1 : 0;
+  // Programmatic dependent launch (RAFT_B200_NO_PDL=1 turns it off): the dependent conv's prologue and its first
+  // weight tiles overlap the tail of this one.  Same-box A/B after the issue-loop fixes: 190 -> 175 us per update step.
+  static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
   cfg.numAttrs = 1 + pdl;
   int stages = Cfg::kStages;
   static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
