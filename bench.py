@@ -299,7 +299,7 @@ def main():
     t_look_warm = ev_time(look, flush_l2=False)
     upd_flops = 2.0 * npix * UPDATE_MAC_PER_PX
     look_bytes = float(npix * LOOKUP_BYTES_PER_PX)
-    roof = {"kernel": "rb_update_step: 10 tcgen05 convs (conv_halo_kernel / conv_tc_kernel) + flow_conv7_kernel", "bound": "tensor",
+    roof = {"kernel": "rb_update_step: 10 tcgen05 convs (conv_tc_kernel, PDL-chained) + flow_conv7_kernel", "bound": "tensor",
             "achieved": upd_flops / t_upd / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
             "frac": upd_flops / t_upd / 1e12 / pk["tf"], "traffic": None, "peak_source": pk["src"],
             "note": "algorithmic fp32-equivalent FLOPs; each product costs 3 fp16 MMAs (hi/lo split), so frac <= 1/3 by design",

@@ -167,6 +167,10 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
     }
   }
   __syncthreads();
+  // PDL: dependents may be scheduled from here on (their own griddepcontrol.wait still waits for this grid to finish);
+  // nothing above touched global memory, everything below comes after the predecessor kernel.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // ---- phase 0: per-unit origin, TMA issue --------------------------------------------------------------
   if (tid < UNITS) {
     const int u = tid, pl = u >> 2, lvl = u & 3;
@@ -323,7 +327,22 @@ static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, con
     attr_set = true;
   }
   dim3 grid((npix + kLookupPB - 1) / kLookupPB), block(kLookupPB * 4 * (2 * R + 1));
-  corr_lookup_kernel<R, SPLIT><<<grid, block, smem, s>>>(pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix);
+  // Programmatic dependent launch (as the convs, conv_tc.cu): inside the iteration loop the lookup follows the flow-head
+  // conv and precedes convc1; its blocks are scheduled while the predecessor drains and wait in griddepcontrol.wait
+  // before they read the coordinates.
+  static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl;
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix));
   RB_CHECK_LAUNCH("corr_lookup_kernel");
   return RB_OK;
 }

@@ -39,6 +39,15 @@ elif a.what == "update":
     capi.check(lib.rb_update_lookup(s, capi.ptr(ws), capi.ptr(pyr), capi.ptr(coords), B, h, w, capi.stream()))
     c1 = coords.clone()
     fn = lambda: capi.check(lib.rb_update_step(s, capi.ptr(blob), capi.ptr(ws), capi.ptr(c1), None, None, B, h, w, capi.stream()))
+elif a.what == "iterate":  # lookup + update step, as inside rb_raft_iterate (4 iterations per call)
+    blob = pack_update_block(synth.make_weights(a.small), a.small, dev)
+    hid, ctx = (96, 64) if a.small else (128, 128)
+    net = torch.tanh(torch.randn(B, h, w, hid, device=dev)); inp = torch.relu(torch.randn(B, h, w, ctx, device=dev))
+    capi.check(lib.rb_update_set_state(s, capi.ptr(blob), capi.ptr(ws), capi.ptr(net), capi.ptr(inp), B, h, w, capi.stream()))
+    c1 = coords.clone()
+    mask = torch.empty(B * h * w * 576, device=dev)
+    fn = lambda: capi.check(lib.rb_raft_iterate(s, capi.ptr(blob), capi.ptr(ws), capi.ptr(pyr), capi.ptr(c1),
+                                                None if a.small else capi.ptr(mask), B, h, w, 4, capi.stream()))
 else:
     raise SystemExit("unknown")
 for _ in range(a.reps):
