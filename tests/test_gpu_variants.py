@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("knob", ["RAFT_B200_HALO", "RAFT_B200_PAIR", "RAFT_B200_CTA2", "RAFT_B200_PDL", "RAFT_B200_NO_HOIST", "RAFT_B200_FUSED"])
+@pytest.mark.parametrize("knob", ["RAFT_B200_HALO", "RAFT_B200_PAIR", "RAFT_B200_CTA2", "RAFT_B200_PDL", "RAFT_B200_NO_HOIST", "RAFT_B200_FUSED", "RAFT_B200_FH2_SIMT", "RAFT_B200_NO_PDL"])
 def test_variant_passes_conv_and_update_parity(cuda, knob):
     env = dict(os.environ, **{knob: "1"})
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_kernels.py"), "-q", "-x",
