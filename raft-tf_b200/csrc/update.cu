@@ -219,15 +219,15 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
 
 // encoder/convf1: 7x7 conv over the 2-channel flow + ReLU (model_utils.py:114,124), CUDA cores
 // (K = 98 is no tensor-core shape).  flow = coords1 - coords_grid (RAFT.py:95) is formed while
-// staging; SAME padding zero-pads the FLOW.  One thread per output channel, 32-pixel row segment
-// per block; the flow itself is also written into the [.., flow] slot of HX/QX (concat_out, :119).
-template <int COUT>
+// staging; SAME padding zero-pads the FLOW.  One thread per output channel, SEG-pixel row segment
+// per block (SEG = 16 at batch 1: 440 blocks instead of 220 -- the kernel is latency-bound, and with the convf2 that
+// follows it on the forked stream it must not finish later than lookup -> convc1 -> convc2 on the main stream); the flow itself is also written into the [.., flow] slot of HX/QX (concat_out, :119).
+template <int COUT, int SEG>
 __global__ void __launch_bounds__(COUT) flow_conv7_kernel(const float2* __restrict__ coords1,
                                                           const float* __restrict__ Wf,  // [98][COUT]
                                                           const float* __restrict__ bf, SplitPtr f1,
                                                           int f1_stride, SplitPtr hx, SplitPtr qx,
                                                           int hx_stride, int flow_choff, int h, int w) {
-  constexpr int SEG = 32;
   __shared__ float2 patch[7][SEG + 6];
   const int x0 = blockIdx.x * SEG, y = blockIdx.y, b = blockIdx.z;
   const int c = threadIdx.x;
@@ -533,12 +533,19 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
   {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
-    dim3 grid((w + 31) / 32, h, B);
+    static const int seg_env = getenv("RAFT_B200_CONV7_SEG") ? atoi(getenv("RAFT_B200_CONV7_SEG")) : 0;  // tuning knob
+    const int seg = seg_env ? seg_env : ((long)B * h * w <= 16384 ? 16 : 32);  // same-box A/B at 55x128: 792 / 772 / 781 us per 4 iterations for 32 / 16 / 8
     const float* Wf = reinterpret_cast<const float*>(bb + L.f1_w);
     const float* bf = reinterpret_cast<const float*>(bb + L.f1_b);
     const float2* c1 = reinterpret_cast<const float2*>(coords1);
-    if (v.small) flow_conv7_kernel<64><<<grid, 64, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
-    else flow_conv7_kernel<128><<<grid, 128, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w);
+#define RB_LAUNCH_CONV7(COUT, SEG) \
+    flow_conv7_kernel<COUT, SEG><<<dim3((w + SEG - 1) / SEG, h, B), COUT, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w)
+    if (v.small) {
+      if (seg == 8) RB_LAUNCH_CONV7(64, 8); else if (seg == 16) RB_LAUNCH_CONV7(64, 16); else RB_LAUNCH_CONV7(64, 32);
+    } else {
+      if (seg == 8) RB_LAUNCH_CONV7(128, 8); else if (seg == 16) RB_LAUNCH_CONV7(128, 16); else RB_LAUNCH_CONV7(128, 32);
+    }
+#undef RB_LAUNCH_CONV7
     RB_CHECK_LAUNCH("flow_conv7_kernel");
     if (!fused) {
       ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
