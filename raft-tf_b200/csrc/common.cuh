@@ -86,6 +86,7 @@ struct ConvParams {
   int ck_begin, ck_count, ck_skip_at, ck_skip;
   const float* addend;  // optional fp32 [pixel][cout] added to the accumulator before bias/activation
   int pdl_early;
+  int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue        // 1: trigger dependents at kernel start instead of at epilogue start (tuning knob)
   long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py
   // packed weights [cout_pad][kh*kw][cin_pad] (K-major) as split planes + fp32 bias

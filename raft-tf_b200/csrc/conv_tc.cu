@@ -409,7 +409,8 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   g.total_tiles = (PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  const int units = PAIR ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
+  int units = PAIR ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
+  if (!PAIR && p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;  // leave SMs to a concurrent conv (update.cu)
   cfg.gridDim = dim3((g.total_tiles < units ? g.total_tiles : units) * (PAIR ? 2 : 1));
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;

@@ -550,6 +550,10 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     if (!fused) {
       ConvParams p = base_params(v, L, blob, P_CONVF2, W.f1, v.f1, 0, B, h, w);
       set_act(p, ACT_RELU, W.cf, v.cf, v.cor);
+      // convf2 runs beside convc1 / convc2 of the main stream: a small CTA budget keeps it off the SMs they need
+      // (batch 1: the other convs use 110 of the 148 SMs; same-box A/B 770 -> 761 us per 4 iterations)
+      static const int lim = getenv("RAFT_B200_CONVF2_CTAS") ? atoi(getenv("RAFT_B200_CONVF2_CTAS")) : -1;  // tuning knob
+      p.cta_limit = lim >= 0 ? lim : ((long)B * h * w <= 16384 ? 38 : 0);
       if ((rc = launch_conv_dbg(p, ss->stream))) return rc;
     }
     RB_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
