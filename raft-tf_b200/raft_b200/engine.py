@@ -43,6 +43,8 @@ class RaftEngine:
             self.blob = pack_update_block(params, small, self.device)
         self._shape = None
         self._graph = None
+        self._enc_stream = None   # forked stream of the context encoder (encode())
+        self._cnet_pending = False
 
     # ---- buffers -------------------------------------------------------------------------------
     def _ensure(self, B: int, H: int, W: int):
@@ -72,17 +74,39 @@ class RaftEngine:
         self._graph = None
 
     # ---- stages --------------------------------------------------------------------------------
-    def encode(self):
-        """RAFT.py:53-59,79-87 on self.images = [left | right]: 2x-1, fnet(left), fnet(right), cnet(left)."""
+    def encode(self, defer_join: bool = False):
+        """RAFT.py:53-59,79-87 on self.images = [left | right]: 2x-1, fnet(left), fnet(right), cnet(left).
+
+        The context encoder is independent of the feature encoder (RAFT.py:79-87) and both are chains of ~50 small
+        kernels at 1/4 and 1/8 resolution: cnet runs on a forked stream beside fnet (a fork/join that is captured into
+        the CUDA graph like the flow branch of the update block).  With defer_join the caller joins (`_join_cnet`)
+        where cmap is first needed -- after the correlation volume, which only needs the feature maps."""
         B = self._shape[0]
         capi.check(capi.lib.rb_set_math_mode(self.math_mode))  # per-thread library state: set before ANY kernel of ours
         if self.torch_encoders:
             both = self.images * 2.0 - 1.0
             self.fmaps.copy_(self.fnet(both))  # instance norm is per sample, so batching left|right is exact
             self.cmap.copy_(self.cnet(both[:B]))
-        else:
+        elif os.environ.get("RAFT_B200_SERIAL_ENCODERS"):
             self.fnet(self.images, out=self.fmaps)
             self.cnet(self.images[:B], out=self.cmap)
+        else:
+            main = torch.cuda.current_stream(self.device)
+            if self._enc_stream is None:
+                self._enc_stream = torch.cuda.Stream(device=self.device)
+            side = self._enc_stream
+            side.wait_stream(main)  # fork: the frames are in place
+            with torch.cuda.stream(side):
+                self.cnet(self.images[:B], out=self.cmap)
+            self.fnet(self.images, out=self.fmaps)
+            self._cnet_pending = True
+            if not defer_join:
+                self._join_cnet()
+
+    def _join_cnet(self):
+        if self._cnet_pending:
+            torch.cuda.current_stream(self.device).wait_stream(self._enc_stream)
+            self._cnet_pending = False
 
     def _hot_path(self):
         """corr build + iterations + upsampling: hand-written kernels only (graph-capturable)."""
@@ -91,6 +115,7 @@ class RaftEngine:
         capi.check(lib.rb_set_math_mode(self.math_mode))
         capi.check(lib.rb_corr_build(capi.ptr(self.fmap1), capi.ptr(self.fmap2), capi.ptr(self.pyramid), B, h, w,
                                      self.fdim, capi.ptr(self.corr_ws), self.cws_bytes, st))
+        self._join_cnet()  # cmap (context encoder, forked stream) is first needed here
         capi.check(lib.rb_update_set_state_cnet(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.cmap), B, h, w, st))
         capi.check(lib.rb_coords_grid(capi.ptr(self.coords1), B, h, w, st))
         capi.check(lib.rb_raft_iterate(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.pyramid),
@@ -102,7 +127,7 @@ class RaftEngine:
                                               B, h, w, st))
 
     def _all(self):
-        self.encode()
+        self.encode(defer_join=True)
         self._hot_path()
 
     def launches_per_forward(self) -> int:

@@ -1,6 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for lim in 0 38 28 55; do
-  echo -n "convf2 ctas=$lim iterate : "; RAFT_B200_CONVF2_CTAS=$lim timeout 300 python tools/micro.py iterate 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_fullsize.py -q -x --timeout 600 2>&1 | tail -2
+for rep in 1 2; do
+echo -n "bench forked cnet : "; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
+echo -n "bench serial enc  : "; RAFT_B200_SERIAL_ENCODERS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
 done
-echo -n "convf2 ctas=0 iterate : "; RAFT_B200_CONVF2_CTAS=0 timeout 300 python tools/micro.py iterate 2>&1 | tail -1
