@@ -86,6 +86,8 @@ struct ConvParams {
   int ck_begin, ck_count, ck_skip_at, ck_skip;
   const float* addend;  // optional fp32 [pixel][cout] added to the accumulator before bias/activation
   int pdl_early;
+  double* stat_part;  // EPI_F32 + tensor-core wide epilogue: per-(sample, strip, channel) sum / sum of squares of the
+  int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue        // 1: trigger dependents at kernel start instead of at epilogue start (tuning knob)
   long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py
@@ -414,9 +416,42 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
   }
 }
 
+// Per-channel sum and sum of squares over the 32 pixels (lanes) of a warp for the 16 channels each lane holds
+// (instance-norm statistics fused into the conv epilogue).  Recursive halving: after the xor-16/8/4/2 exchanges lane l
+// owns channel 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of l), the xor-1 step completes the sum; 32 shuffles, fixed order.
+__device__ __forceinline__ void warp_stats16(const float* y, float& s, float& s2, int& ch) {
+  const unsigned lane = threadIdx.x & 31u;
+  float a[8], b[8];
+  {
+    const bool up = (lane & 16u) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float keep = up ? y[i + 8] : y[i], send = up ? y[i] : y[i + 8];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      b[i] = keep * keep + __shfl_xor_sync(0xffffffffu, send * send, 16);
+    }
+  }
+#pragma unroll
+  for (int w = 4; w >= 1; w >>= 1) {  // 8 -> 4 -> 2 -> 1 values per lane, partner at xor 2w
+    const bool up = (lane & (unsigned)(2 * w)) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float ka = up ? a[i + w] : a[i], sa = up ? a[i] : a[i + w];
+      const float kb = up ? b[i + w] : b[i], sb = up ? b[i] : b[i + w];
+      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, 2 * w);
+      b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, 2 * w);
+    }
+  }
+  s = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+  s2 = b[0] + __shfl_xor_sync(0xffffffffu, b[0], 1);
+  ch = (int)(((lane >> 4) & 1u) * 8u + ((lane >> 3) & 1u) * 4u + ((lane >> 2) & 1u) * 2u + ((lane >> 1) & 1u));
+}
+
 // back ends
 int launch_conv_simt(const ConvParams& p, cudaStream_t s);
 int launch_conv_tc(const ConvParams& p, cudaStream_t s);
+int conv_tc_tiles_per_image(int h, int w);
+bool conv_tc_fused_stats_ok(const ConvParams& p);
 inline int launch_conv(const ConvParams& p, cudaStream_t s) {
   return math_mode() == RB_MATH_SIMT ? launch_conv_simt(p, s) : launch_conv_tc(p, s);
 }

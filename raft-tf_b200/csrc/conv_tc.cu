@@ -255,6 +255,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
             }
           }
+          if (p.stat_part) {  // instance-norm statistics of the values just stored (v was finalised in place; host: wide only)
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            float s1, s2;
+            int ch;
+            warp_stats16(v, s1, s2, ch);
+            if ((lane & 1) == 0 && mt < g.m_tiles) {
+              double* dst = p.stat_part + ((size_t)(b * p.stat_strips + trem * 4 + q) * 2) * p.cout + n0 + c + ch;
+              dst[0] = (double)s1;
+              dst[p.cout] = (double)s2;
+            }
+          }
         }
         // this warp no longer needs the accumulator buffer: hand it back to the MMA warp
         tc_fence_before();
@@ -370,6 +384,19 @@ static TileGeom choose_geom(int h, int w) {
   return best;
 }
 
+// Pixel tiles per image of the tensor-core conv (strip count of the fused instance-norm statistics = 4x this).
+int conv_tc_tiles_per_image(int h, int w) {
+  const TileGeom g = choose_geom(h, w);
+  return g.tiles_x * g.tiles_y;
+}
+// The conv can produce the statistics itself: tensor-core back end, 16-channel epilogue (see epilogue_wide_ok()).
+bool conv_tc_fused_stats_ok(const ConvParams& p) {
+  static const bool off = getenv("RAFT_B200_NO_FUSED_STATS") != nullptr;  // A/B knob
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  return !off && math_mode() == RB_MATH_TC && p.epi == EPI_F32 && (p.cout & 15) == 0 && al(p.bias) && al(p.addend) && al(p.f0) &&
+         p.cin_pad % kChunkK == 0;
+}
+
 // cycles per 16-wide k-slice: max(tensor math, shared-memory operand reads), see DESIGN.md
 static int slice_cycles(int n) {
   int math = n + n / 2;
@@ -471,7 +498,7 @@ int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
 }
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
-  if (p.kh * p.kw > 1) {  // multi-tap convs: halo-tile kernel (each input pixel is fetched once per tap ROW, not per tap)
+  if (p.kh * p.kw > 1 && !p.stat_part) {  // multi-tap convs: halo-tile kernel (each input pixel is fetched once per tap ROW, not per tap)
     bool handled = false;
     int rc = launch_conv_halo(p, s, &handled);
     if (rc || handled) return rc;
@@ -481,7 +508,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
   const int bn = choose_block_n(p.cout, m_tiles);
-  {
+  if (!p.stat_part) {
     bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
     int rc = launch_conv_tc2(p, s, bn, g.bw_log2, g.bh_log2, g.tiles_x, g.tiles_y, &handled);
     if (rc || handled) return rc;

@@ -279,7 +279,8 @@ struct EncWs {
   SplitPtr act[4];  // rotating activation buffers
   SplitPtr col;     // gathered patches of strided convs
   float* f32;       // raw conv output awaiting instance norm
-  double* part;
+  double* part;     // instance-norm partial sums [B][strips][2][C]
+  size_t part_cap;  // strips * C it can hold per sample
   float2* stat;
   size_t total;
 };
@@ -301,7 +302,10 @@ static EncWs enc_ws_layout(int small, int B, int H, int W, void* base) {
   w.col.hi = reinterpret_cast<__half*>(b + off); off += col_plane;
   w.col.lo = reinterpret_cast<__half*>(b + off); off += col_plane;
   w.f32 = reinterpret_cast<float*>(b + off); off += al(px2 * (size_t)(small ? 64 : 128) * sizeof(float));
-  w.part = reinterpret_cast<double*>(b + off); off += al((size_t)B * kStrips * 2 * 256 * sizeof(double));
+  // strips: kStrips for the stand-alone statistics pass, 4 per pixel tile when the conv epilogue produces them
+  const size_t fused_cap = (size_t)4 * conv_tc_tiles_per_image((H + 1) / 2, (W + 1) / 2) * 128;
+  w.part_cap = fused_cap > (size_t)kStrips * 256 ? fused_cap : (size_t)kStrips * 256;
+  w.part = reinterpret_cast<double*>(b + off); off += al((size_t)B * w.part_cap * 2 * sizeof(double));
   w.stat = reinterpret_cast<float2*>(b + off); off += al((size_t)B * 256 * sizeof(float2));
   (void)c0;
   w.total = off;
@@ -372,13 +376,23 @@ static int enc_conv(const EncRun& R, int i, const float* img, SplitPtr in, int i
     if ((rc = launch_conv(p, R.s))) return rc;
   } else if (inorm) {
     p.epi = EPI_F32; p.f0 = R.ws.f32;
-    if ((rc = launch_conv(p, R.s))) return rc;
     const int npx = oh * ow, C = pk.cout;
-    const int rows = max(1, 256 / C);
-    dim3 g1(kStrips, R.B);
-    inorm_partial_kernel<<<g1, rows * C, 2 * rows * C * sizeof(double), R.s>>>(R.ws.f32, R.ws.part, npx, C, kStrips);
-    RB_CHECK_LAUNCH("inorm_partial_kernel");
-    inorm_final_kernel<<<dim3(C, R.B), 256, 0, R.s>>>(R.ws.part, R.ws.stat, npx, C, kStrips);
+    // statistics, stage 1: by the conv's own epilogue (per pixel tile and lane quarter) when it runs on the tensor-core
+    // kernel with the 16-channel epilogue, else by a pass over the fp32 output
+    int strips = kStrips;
+    const int fused_strips = 4 * conv_tc_tiles_per_image(oh, ow);
+    if (conv_tc_fused_stats_ok(p) && (size_t)fused_strips * C <= R.ws.part_cap) {
+      p.stat_part = R.ws.part;
+      p.stat_strips = strips = fused_strips;
+    }
+    if ((rc = launch_conv(p, R.s))) return rc;
+    if (!p.stat_part) {
+      const int rows = max(1, 256 / C);
+      dim3 g1(kStrips, R.B);
+      inorm_partial_kernel<<<g1, rows * C, 2 * rows * C * sizeof(double), R.s>>>(R.ws.f32, R.ws.part, npx, C, kStrips);
+      RB_CHECK_LAUNCH("inorm_partial_kernel");
+    }
+    inorm_final_kernel<<<dim3(C, R.B), 256, 0, R.s>>>(R.ws.part, R.ws.stat, npx, C, strips);
     RB_CHECK_LAUNCH("inorm_final_kernel");
     size_t n = (size_t)R.B * npx * (C / 8);
     inorm_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, R.s>>>(R.ws.f32, R.ws.stat, res.hi, res.lo, res_stride, dst.hi,
