@@ -305,8 +305,8 @@ def main():
             "note": "algorithmic fp32-equivalent FLOPs; each product costs 3 fp16 MMAs (hi/lo split), so frac <= 1/3 by design",
             "us_per_launch_group": t_upd * 1e6}
     roof_l = {"kernel": "corr_lookup_kernel<4,split>", "bound": "hbm", "achieved": look_bytes / t_look / 1e9,
-              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": 35.63e6 * B,
-              "traffic_note": "ncu --set full (profiles/r01_lookup_ncu_full.txt): dram read 35.6 MB + write 0.05 MB per cold launch",
+              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": 38.10e6 * B,
+              "traffic_note": "ncu --set full (profiles/r01_lookup_ncu_full.txt): dram read 38.05 MB + write 0.05 MB per cold launch (TMA boxes of 16 columns: whole 64-byte rows)",
               "peak_source": pk["src"], "us_per_launch": t_look * 1e6,
               "l2_warm": {"us_per_launch": t_look_warm * 1e6, "achieved": look_bytes / t_look_warm / 1e9,
                           "note": "same launch without the L2 flush: at B=1 the ~25 MB of patches around the current flow stay L2-resident between iterations"}}
