@@ -86,6 +86,7 @@ struct ConvParams {
   int ck_begin, ck_count, ck_skip_at, ck_skip;
   const float* addend;  // optional fp32 [pixel][cout] added to the accumulator before bias/activation
   int pdl_early;
+  const float* flow_tail;  // EPI_ACT, 16-channel epilogue: coords1; the last two channels are written as flow = coords1 - grid
   double* stat_part;  // EPI_F32 + tensor-core wide epilogue: per-(sample, strip, channel) sum / sum of squares of the
   int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
@@ -368,6 +369,14 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
       if (p.act == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      if (p.flow_tail && c + 16 == p.cout) {
+        // motion encoder: [126 conv channels | flow] (model_utils.py:119) -- the flow slot completes the 16-channel group,
+        // same arithmetic as flow_conv7_kernel (coords1 - coords_grid, RAFT.py:95)
+        const int x = pix % p.w, yy = (pix / p.w) % p.h;
+        const float2 cc = *reinterpret_cast<const float2*>(p.flow_tail + (size_t)pix * 2);
+        y[14] = cc.x - (float)x;
+        y[15] = cc.y - (float)yy;
       }
       store_split16(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + c, y);
       if (p.d1_hi) store_split16(p, p.d1_hi, p.d1_lo, (size_t)pix * p.d1_stride + p.d1_choff + c, y);

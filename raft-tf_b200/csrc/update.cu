@@ -598,6 +598,12 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     ConvParams p = base_params(v, L, blob, P_MOTION, W.cf, v.cf, 0, B, h, w);
     set_act(p, ACT_RELU, W.hx, v.hx, xoff);
     p.d1_hi = W.qx.hi; p.d1_lo = W.qx.lo; p.d1_stride = v.hx; p.d1_choff = xoff;
+    if (math_mode() == RB_MATH_TC && (p.cout & 15) == 14 && p.cout + 2 <= p.cout_pad && foff == xoff + p.cout) {
+      // things: 126 channels + the 2 flow channels right behind them = one full 16-channel group -> the tensor-core
+      // epilogue writes the flow slot too and takes its 256-bit path (the weight rows / biases 126,127 are zero)
+      p.cout += 2;
+      p.flow_tail = coords1;
+    }
     if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   // ---- GRU (model_utils.py:138-169) ----
