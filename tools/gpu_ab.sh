@@ -1,7 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e.py tests/test_gpu_fullsize.py -q -x --timeout 600 2>&1 | tail -2
-for rep in 1 2; do
-  echo -n "iterate x4 new : "; timeout 300 python tools/micro.py iterate 2>&1 | tail -1
-  echo -n "iterate x4 prev: "; RAFT_B200_LIB=$PWD/raft-tf_b200/lib/libraft_b200_prev.so timeout 300 python tools/micro.py iterate 2>&1 | tail -1
-done
+timeout 1500 python -m pytest tests/test_gpu_variants.py -q -x --timeout 1500 2>&1 | tail -2
+timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_default.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['us_per_launch_group'], d['roofline_lookup']['frac'], d['cpu_baseline'], d['clocks'], d['gpu_launches'])"
+bash tools/batch_sweep.sh 2>&1 | tee gpurun_out/batch_sweep.log
