@@ -1,5 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 1500 python -m pytest tests/test_gpu_variants.py -q -x --timeout 1500 2>&1 | tail -2
-timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_default.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['us_per_launch_group'], d['roofline_lookup']['frac'], d['cpu_baseline'], d['clocks'], d['gpu_launches'])"
-bash tools/batch_sweep.sh 2>&1 | tee gpurun_out/batch_sweep.log
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e.py tests/test_gpu_fullsize.py -q -x --timeout 600 2>&1 | tail -3
+for rep in 1 2; do
+  echo -n "iterate x4 fused flow head : "; timeout 300 python tools/micro.py iterate 2>&1 | tail -1
+  echo -n "iterate x4 two convs       : "; RAFT_B200_NO_FH_FUSE=1 timeout 300 python tools/micro.py iterate 2>&1 | tail -1
+done
+echo -n "B=8 fused : "; timeout 300 python tools/micro.py iterate --B 8 2>&1 | tail -1
+echo -n "B=8 two   : "; RAFT_B200_NO_FH_FUSE=1 timeout 300 python tools/micro.py iterate --B 8 2>&1 | tail -1
