@@ -1,9 +1,11 @@
 #!/bin/bash
+# Same-box A/B template: one knob on/off on the micro benchmarks (update step, lookup + update step), B = 1 and 8.
+#   usage: tools/gpu_ab.sh RAFT_B200_NO_PDL      (any environment knob of README.md)
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e.py tests/test_gpu_fullsize.py -q -x --timeout 600 2>&1 | tail -3
-for rep in 1 2; do
-  echo -n "iterate x4 fused flow head : "; timeout 300 python tools/micro.py iterate 2>&1 | tail -1
-  echo -n "iterate x4 two convs       : "; RAFT_B200_NO_FH_FUSE=1 timeout 300 python tools/micro.py iterate 2>&1 | tail -1
+knob=${1:-RAFT_B200_NO_PDL}
+for args in "" "--B 8"; do
+  for what in update iterate; do
+    echo -n "default      $what $args : "; timeout 300 python tools/micro.py $what $args 2>&1 | tail -1
+    echo -n "$knob=1 $what $args : "; env $knob=1 timeout 300 python tools/micro.py $what $args 2>&1 | tail -1
+  done
 done
-echo -n "B=8 fused : "; timeout 300 python tools/micro.py iterate --B 8 2>&1 | tail -1
-echo -n "B=8 two   : "; RAFT_B200_NO_FH_FUSE=1 timeout 300 python tools/micro.py iterate --B 8 2>&1 | tail -1
