@@ -52,7 +52,9 @@ struct TcCfg {
 // PAIR = true: CTAs are launched as clusters of two that work on two pixel tiles of the SAME cout tile; CTA 0 fetches
 // B_hi, CTA 1 fetches B_lo, each with TMA multicast into both CTAs' shared memory, so every SM issues only half of
 // the weight-tile requests (the measured bound of the MMA loop is the ~38 B/clk a single SM can request from L2).
-template <int BLOCK_N, bool PAIR>
+// EXTRAS: phase timestamps (p.dbg) and fused instance-norm statistics (p.stat_part) -- a separate instantiation, so that
+// the kernel the update block runs stays below the 96-register cap of a 576-thread CTA without spills.
+template <int BLOCK_N, bool PAIR, bool EXTRAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -67,7 +69,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  long long* dbg = (EXTRAS && p.dbg) ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
   const bool wide = epilogue_wide_ok(p);
   if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   const int chunks = conv_chunks(p);
@@ -255,7 +257,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
             }
           }
-          if (p.stat_part) {  // instance-norm statistics of the values just stored (v was finalised in place; host: wide only)
+          if (EXTRAS && p.stat_part) {  // instance-norm statistics of the values just stored (v was finalised in place; host: wide only)
             if (!valid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -425,7 +427,8 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     int dev = 0;
     RB_CHECK_CUDA(cudaGetDevice(&dev));
     RB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -457,7 +460,10 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   int stages = Cfg::kStages;
   static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
   if (env_stages > 0 && env_stages < stages) stages = env_stages;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, PAIR>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
+  if (p.dbg || p.stat_part)
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, PAIR, true>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
+  else
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, PAIR, false>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
