@@ -172,8 +172,11 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // ---- phase 0: per-unit origin, TMA issue --------------------------------------------------------------
-  if (tid < UNITS) {
-    const int u = tid, pl = u >> 2, lvl = u & 3;
+  // The 64 units are spread over the first lanes of ALL warps: every lane issues its own TMA with its own operands,
+  // which ptxas serialises per warp (one elect / R2UR round per distinct lane) -- 4-5 rounds per warp instead of 32 in 2.
+  constexpr int kWarps = NT / 32, kUnitsPerWarp = (UNITS + kWarps - 1) / kWarps;
+  if ((tid & 31) < kUnitsPerWarp && (tid >> 5) * kUnitsPerWarp + (tid & 31) < UNITS) {
+    const int u = (tid >> 5) * kUnitsPerWarp + (tid & 31), pl = u >> 2, lvl = u & 3;
     const int pix = min(pix0 + pl, npix - 1);
     const float2 c = __ldg(coords + pix);
     const float inv = 1.0f / (float)(1 << lvl);  // centroid / 2**i (model_utils.py:239), exact
