@@ -406,7 +406,7 @@ static int slice_cycles(int n) {
   return math > smem ? math : smem;
 }
 
-static int choose_block_n(int cout, long m_tiles) {
+static int choose_block_n(int cout, long m_tiles, int ctas = 148) {  // ctas: persistent CTAs the launch may use (cta_limit)
   if (cout <= 16) return 16;
   const int cand[4] = {128, 96, 64, 32};
   int best = 128;
@@ -414,7 +414,7 @@ static int choose_block_n(int cout, long m_tiles) {
   for (int i = 0; i < 4; ++i) {
     int n = cand[i];
     long tiles = m_tiles * ((cout + n - 1) / n);
-    long waves = (tiles + 147) / 148;
+    long waves = (tiles + ctas - 1) / ctas;
     long cost = waves * slice_cycles(n);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = n; }
   }
@@ -477,7 +477,7 @@ int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   TileGeom g = choose_geom(p.h, p.w);
   g.m_tiles = p.B * g.tiles_x * g.tiles_y;
-  const int bn = choose_block_n(p.cout, g.m_tiles);
+  const int bn = choose_block_n(p.cout, g.m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
   g.n_tiles = (p.cout + bn - 1) / bn;
   g.total_tiles = g.m_tiles * g.n_tiles;
   job->p = p;
@@ -513,7 +513,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
-  const int bn = choose_block_n(p.cout, m_tiles);
+  const int bn = choose_block_n(p.cout, m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
   if (!p.stat_part) {
     bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
     int rc = launch_conv_tc2(p, s, bn, g.bw_log2, g.bh_log2, g.tiles_x, g.tiles_y, &handled);
