@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
             if (valid && !(J.whatif & 32)) {
               if (wide) {
-                epilogue_wide16(p, pix, n0 + c, v);
+                epilogue_wide16<true>(p, pix, n0 + c, v);
               } else {
                 epilogue_store<8>(p, pix, n0 + c, v);
                 epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
