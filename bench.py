@@ -44,6 +44,11 @@ UPDATE_MAC_PER_PX = 2675968
 LOOKUP_BYTES_PER_PX = 2904  # N*[4*((2r+2)^2*4 + (2r+1)^2*4) + 8], r=4, fp32 volume, fp32-equivalent output
 
 
+def workload(b_per_gpu=1):
+    """config.workload -- the SAME string in both arms (the driver compares them)."""
+    return f"raft-things B={b_per_gpu}/GPU {H_IMG}x{W_IMG} (padded {H_PAD}x{W_PAD}) {ITERS} iters"
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -115,29 +120,25 @@ def effective_cores():
     return n
 
 
-CPU_SAMPLE_ITERS = 4
-
-
 def cpu_sample(threads):
-    """Bounded sample of the workload on the host CPU: the full 440x1024 pair through encoders + correlation
-    pyramid (once) and CPU_SAMPLE_ITERS of the 32 iterations; the per-pair time is extrapolated linearly in the
-    iteration count (iterations are identical in cost).  Returns (seconds per pair, description)."""
+    """One step of the workload on the host CPU: the full 440x1024 pair through encoders, correlation pyramid, ALL 32
+    iterations and the convex upsampling of the CPU oracle (torch fp32 restatement of the reference; nothing is
+    extrapolated).  Returns (seconds per pair, description)."""
     from oracle.raft_oracle import RAFTOracle, upsample_flow
     from raft_b200 import synth
     torch.set_num_threads(threads)
     params = synth.make_weights(SMALL)
     l, r = synth.make_batch(1, H_PAD, W_PAD)
-    m = RAFTOracle(params, small=SMALL, iters=CPU_SAMPLE_ITERS)
+    m = RAFTOracle(params, small=SMALL, iters=ITERS)
     t0 = time.perf_counter()
     st = m.prepare(torch.from_numpy(l), torch.from_numpy(r))
     t1 = time.perf_counter()
     net, mask, c1 = m.iterate(st)
     upsample_flow(c1 - st["coords0"], mask)
     t2 = time.perf_counter()
-    t_pair = (t1 - t0) + (t2 - t1) * (ITERS / CPU_SAMPLE_ITERS)
-    desc = (f"1 frame pair {H_PAD}x{W_PAD}: encoders + volume {t1 - t0:.2f}s measured once, {CPU_SAMPLE_ITERS} of {ITERS} "
-            f"iterations measured ({t2 - t1:.2f}s) and scaled x{ITERS // CPU_SAMPLE_ITERS}; torch-CPU fp32 oracle, {threads} threads")
-    return t_pair, desc
+    desc = (f"1 frame pair {H_PAD}x{W_PAD}, all {ITERS} iterations measured (encoders + volume {t1 - t0:.2f}s, iterations + "
+            f"upsampling {t2 - t1:.2f}s); torch-CPU fp32 oracle, {threads} threads")
+    return t2 - t0, desc
 
 
 def run_reference(args, rank, world):
@@ -159,12 +160,75 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"raft-things B=1 {H_IMG}x{W_IMG} (padded {H_PAD}x{W_PAD}) {ITERS} iters",
-                       "note": "CPU restatement of gonglixue/RAFT-tf (TensorFlow/tensorpack not installable offline)"},
+            "config": {"workload": workload(1), "global_batch": 1,
+                       "note": "CPU restatement of gonglixue/RAFT-tf (TensorFlow/tensorpack not installable offline); "
+                               "one process on the host cores whatever --gpus says"},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def other_configs(args, rank, world, dev, timed, dist):
+    """BASELINE.json configs[2..4] on the launched GPUs, batch-sharded: every rank runs its slice of the
+    global batch, the [B/G,H,W,2] flows are all_gathered over NCCL so that each rank holds the full result.
+
+      config3  raft-things  B=8          540x960 (-> 544x960), 32 it   -- single-GPU config: N=1 only
+      config4  raft-things  B=4 per GPU  436x1024, 32 it               -- 32 pairs over 8 GPUs
+      config5  raft-small   B=8 per GPU  768x1024, 20 it               -- 64 pairs over 8 GPUs
+
+    value = global pairs/s with frames resident (max over ranks); e2e = pinned-host frames in, H2D + forward + NCCL
+    all_gather + D2H of this rank's shard inside the timed span; gather_us = the all_gather alone (CUDA events)."""
+    from types import SimpleNamespace
+    from raft_b200 import synth
+    from networks.RAFT import RAFT
+    specs = [("config4", False, 4, 436, 1024, 32), ("config5", True, 8, 768, 1024, 20)]
+    if world == 1:
+        specs.insert(0, ("config3", False, 8, 540, 960, 32))
+    out = {}
+    steps = max(3, min(args.steps, 5))
+    for name, small, b, H, W, iters in specs:
+        try:
+            m = RAFT((H, W, 3), SimpleNamespace(small=small), iters=iters, batch=b, device=dev).load(synth.make_weights(small))
+            l_np, r_np = synth.make_batch(b, H, W, seed0=2000 + rank * b)
+            lh, rh = torch.from_numpy(l_np).pin_memory(), torch.from_numpy(r_np).pin_memory()
+            ld, rd = lh.to(dev), rh.to(dev)
+            oh = torch.empty(b, H, W, 2, dtype=torch.float32).pin_memory()
+            full = torch.empty(world * b, H, W, 2, dtype=torch.float32, device=dev)
+            gev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+            def gather(flow):
+                if world > 1:
+                    gev[0].record()
+                    dist.all_gather_into_tensor(full, flow.contiguous())
+                    gev[1].record()
+
+            def res():
+                gather(m.engine().forward(ld, rd))
+
+            def e2e():
+                flow = m.engine().forward(lh, rh)
+                gather(flow)
+                oh.copy_(flow, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(2):
+                res(); e2e()
+            t_r, t_e = timed(res, steps), timed(e2e, steps)
+            pairs = b * world * steps
+            g_us = None
+            if world > 1:
+                torch.cuda.synchronize()
+                g_us = gev[0].elapsed_time(gev[1]) * 1e3
+            out[name] = {"workload": f"raft-{'small' if small else 'things'} B={b}/GPU {H}x{W} {iters} iters",
+                         "global_batch": b * world, "value": pairs / t_r, "unit": "pairs/s", "ms_per_step": t_r / steps * 1e3,
+                         "e2e": {"value": pairs / t_e, "h2d_bytes_per_step": int(lh.numel() * 8), "d2h_bytes_per_step": int(oh.numel() * 4),
+                                 "ms_per_step": t_e / steps * 1e3},
+                         "gather_us": g_us, "gather_bytes_per_rank": int(b * H * W * 8) if world > 1 else 0, "steps": steps}
+            del m, ld, rd, full
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 -- an extra: never lose the headline line for it
+            out[name] = {"error": str(e)[:300]}
+    return out
 
 
 def main():
@@ -175,6 +239,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs (other_configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -326,6 +391,38 @@ def main():
     except Exception as e:  # noqa: BLE001 -- an extra, never fail the bench line for it
         roof_l["batch8"] = {"error": str(e)[:200]}
 
+    # ---- correlation build (A1): four tcgen05 GEMMs + operand split / pooling passes; the 261 MB fp32 volume write is its
+    # HBM side, 2*N^2*C*(1+1/4+1/16+1/64) its tensor side ("balanced; report both")
+    t_corr = ev_time(lambda: capi.check(lib.rb_corr_build(capi.ptr(eng.fmap1), capi.ptr(eng.fmap2), capi.ptr(eng.pyramid), B, h, w,
+                                                          eng.fdim, capi.ptr(eng.corr_ws), eng.cws_bytes, capi.stream())), reps=5)
+    N1 = h * w
+    lvl_elems = sum((h >> l) * (w >> l) for l in range(4))
+    corr_bytes = float(B * (2 * N1 * eng.fdim * 4 + N1 * lvl_elems * 4))
+    corr_flops = 2.0 * B * N1 * lvl_elems * eng.fdim
+    roof_c = {"kernel": "rb_corr_build: conv_tc_kernel x4 (volume + 3 pooled levels by linearity) + split/pool passes",
+              "bound": "hbm", "achieved": corr_bytes / t_corr / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+              "frac": corr_bytes / t_corr / 1e9 / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+              "us_per_launch_group": t_corr * 1e6, "algorithmic_bytes": corr_bytes,
+              "tensor": {"achieved": corr_flops / t_corr / 1e12, "unit": "TFLOP/s (fp32-equivalent; 3 fp16 MMAs per product)",
+                         "frac": corr_flops / t_corr / 1e12 / pk["tf"]}}
+
+    # ---- e2e with uint8 host frames (what cv2.imdecode yields; /255 on the GPU): 4x fewer H2D bytes ----
+    l8 = torch.from_numpy(np.round(l_np * 255.0).astype(np.uint8)).pin_memory()
+    r8 = torch.from_numpy(np.round(r_np * 255.0).astype(np.uint8)).pin_memory()
+
+    def step_e2e_u8():
+        flow = model.forward(l8, r8)
+        out_host.copy_(flow, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(2):
+        step_e2e_u8()
+    t_e2e_u8 = timed(step_e2e_u8, args.steps)
+
+    # ---- the other BASELINE.json configurations, batch-sharded as SURVEY 8(e) specifies ----
+    others = {}
+    if not args.headline_only:
+        others = other_configs(args, rank, world, dev, timed, dist)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(effective_cores(), 32)
@@ -340,13 +437,17 @@ def main():
                 "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split operands, fp32 accumulate)",
                 "data": "synthetic",
-                "config": {"workload": f"raft-things B={B}/GPU {H_IMG}x{W_IMG} (padded {H_PAD}x{W_PAD}) {ITERS} iters",
-                           "global_batch": B * world, "parallelism": f"dp{world}",
+                "config": {"workload": workload(B), "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "flushed between steps (256 MiB write)", "weights": "seeded random (synth.make_weights)"},
                 "e2e": {"value": pairs / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes,
                         "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": t_e2e / args.steps * 1e3},
                 "gpu_launches": launches_per_fwd * args.steps, "gpu_launches_per_step": launches_per_fwd,
-                "roofline": roof, "roofline_lookup": roof_l, "clocks": clk}
+                "roofline": roof, "roofline_lookup": roof_l, "roofline_corr": roof_c, "clocks": clk}
+        line["e2e"]["u8_frames"] = {"value": pairs / t_e2e_u8, "unit": "pairs/s", "h2d_bytes_per_step": int(l8.numel() * 2),
+                                    "ms_per_step": t_e2e_u8 / args.steps * 1e3,
+                                    "note": "same call with uint8 BGR host frames (cv2.imdecode's type); x/255 on the GPU"}
+        if others:
+            line["other_configs"] = others
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

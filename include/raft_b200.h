@@ -139,6 +139,20 @@ int rb_upsample_convex(const float* coords1, const float* mask, float* out, int 
                        void* stream);
 /* scale = 1.0 reproduces the reference (no x8, utils.py:110); upstream RAFT would pass 8.0. */
 int rb_upflow8(const float* coords1, float* out, int B, int h, int w, float scale, void* stream);
+/* Cropped forms: out is [B,out_h,out_w,2] = rows [top, top+out_h) x cols [left, left+out_w) of the 8h x 8w field
+ * (frames that rb_frames_prepare padded to a multiple of 8 are cropped back by the upsampling kernel itself). */
+int rb_upsample_convex_crop(const float* coords1, const float* mask, float* out, int B, int h, int w,
+                            int top, int left, int out_h, int out_w, void* stream);
+int rb_upflow8_crop(const float* coords1, float* out, int B, int h, int w, float scale, int top, int left,
+                    int out_h, int out_w, void* stream);
+
+/* ---- F3 (input edge): dataflow/test_dataflow.py:56-61,96-97 + the SURVEY 8(d) shape policy ------------------
+ * src: [B,H,W,3] device frames, BGR like cv2.imdecode -- fp32 in [0,1] (src_is_u8 = 0) or uint8 in [0,255]
+ * (src_is_u8 = 1: x/255.0f, the reference's np.float32(x)/255.0, bit for bit).  dst: [B,H+pt+pb,W+pl+pr,3] fp32
+ * in [0,1], replicate-padded (upstream InputPadder; the caller chooses the split).  The 2x-1 of
+ * RAFT.input_preprocess (RAFT.py:53-59) is applied inside rb_encoder_forward. */
+int rb_frames_prepare(const void* src, int src_is_u8, float* dst, int B, int H, int W, int pad_top,
+                      int pad_bottom, int pad_left, int pad_right, void* stream);
 
 /* ---- F1: BasicEncoder / SmallEncoder  networks/model_utils.py:61-105 (+ input_preprocess RAFT.py:53-59) --
  * norm: 0 = 'none', 1 = 'instance' (fnet), 2 = 'batch' (cnet of raft-things; folded into the convs at pack

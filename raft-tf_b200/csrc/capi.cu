@@ -16,6 +16,21 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { ++g_launches; }
 int math_mode() { return g_mode; }
+
+int current_device(int* dev) {
+  RB_CHECK_CUDA(cudaGetDevice(dev));
+  return RB_OK;
+}
+int device_sm_count(int dev) {
+  static int cache[256];  // 0 = not queried yet; racing first calls write the same value
+  if (dev < 0 || dev >= 256) return 148;
+  int n = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    __atomic_store_n(&cache[dev], n, __ATOMIC_RELAXED);
+  }
+  return n;
+}
 }  // namespace rb
 
 extern "C" int rb_version(void) { return 100; }

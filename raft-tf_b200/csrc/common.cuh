@@ -15,6 +15,16 @@ void set_error(const char* fmt, ...);
 void count_launch();
 int math_mode();
 
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) and the SM count are PER DEVICE: a process may
+// drive several GPUs (RaftEngine(device=...)), so "already set" is tracked per (call site, device ordinal).
+struct PerDeviceOnce {
+  unsigned long long done[4] = {0, 0, 0, 0};  // bit per device ordinal (<= 256 devices); racing first calls are idempotent
+  bool test(int dev) const { return (__atomic_load_n(&done[(dev >> 6) & 3], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull; }
+  void set(int dev) { __atomic_fetch_or(&done[(dev >> 6) & 3], 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+int current_device(int* dev);   // cudaGetDevice with error plumbing
+int device_sm_count(int dev);   // cached cudaDevAttrMultiProcessorCount (148 on B200)
+
 #define RB_CHECK_CUDA(expr)                                                                   \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -50,7 +60,11 @@ int math_mode();
 constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
 
+// Range: fp16 planes hold |a| <= 65504.  Larger magnitudes SATURATE (finite, wrong) instead of turning into inf -> NaN
+// through the tensor-core path; the host side refuses weights outside the range (raft_b200/weights.py) and the engine
+// checks the fp32 tensors at the boundary of the split path on the first forward of a weight set (engine.py).
 __host__ __device__ inline void split_f32(float a, __half& hi, __half& lo) {
+  a = fminf(fmaxf(a, -65504.0f), 65504.0f);
   hi = __float2half_rn(a);
   lo = __float2half_rn((a - __half2float(hi)) * kLoScale);
 }
@@ -309,6 +323,8 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
 // ---- lean 16-channel epilogue (tensor-core kernels, epilogue_wide_ok() launches) ----------------------------------
 // Same arithmetic as epilogue_store<NV>, element for element; 256-bit global accesses, no per-element bounds logic.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.0f), 65504.0f);  // saturate like split_f32
+  b = fminf(fmaxf(b, -65504.0f), 65504.0f);
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);

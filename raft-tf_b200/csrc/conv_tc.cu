@@ -321,10 +321,19 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  const CUtensorMapDataType dt = kind == TMAP_F32_SW64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const CUtensorMapSwizzle sw = kind == TMAP_F32_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapDataType dt = kind == TMAP_F16_SW128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = kind == TMAP_F32_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : kind == TMAP_F32_PLAIN ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
+  // L2 promotion: 256-byte requests suit the dense 128-byte operand rows of the GEMM tiles; the lookup's 48-byte patch
+  // rows are a gather (r01: 1.86x the algorithmic DRAM bytes) -> none.  RAFT_B200_LOOKUP_L2PROMO = 0/64/128/256: A/B knob.
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (kind == TMAP_F32_PLAIN) {
+    static const int env = getenv("RAFT_B200_LOOKUP_L2PROMO") ? atoi(getenv("RAFT_B200_LOOKUP_L2PROMO")) : 0;
+    promo = env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+            : env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  }
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RB_REQUIRE(r == CUDA_SUCCESS, RB_ERR_CUDA,
              "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
@@ -424,16 +433,15 @@ static int choose_block_n(int cout, long m_tiles, int ctas = 148) {  // ctas: pe
 template <int BLOCK_N, bool PAIR>
 static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = TcCfg<BLOCK_N>;
-  static bool attr_set = false;
-  static int num_sms = 148;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  int dev = 0, rc_dev;
+  if ((rc_dev = current_device(&dev))) return rc_dev;
+  if (!attr_set.test(dev)) {
     RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    int dev = 0;
-    RB_CHECK_CUDA(cudaGetDevice(&dev));
-    RB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true;
+    attr_set.set(dev);
   }
+  const int num_sms = device_sm_count(dev);
   g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
   g.m_tiles = p.B * g.tiles_x * g.tiles_y;
   g.total_tiles = (PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
@@ -468,10 +476,13 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   return RB_OK;
 }
 
+#ifdef RB_EXPERIMENTS  // measured-slower variants (csrc/experiments/, profiles/r01_notes.md): only in libraft_b200_exp.so
 int launch_conv_halo(const ConvParams& p, cudaStream_t s, bool* handled);
 int launch_conv_tc2(const ConvParams& p, cudaStream_t s, int bn, int bw_log2, int bh_log2, int tiles_x, int tiles_y, bool* handled);
+#endif
 
-// Geometry, tile width and tensor maps of one conv for the fused update-step kernel (update_fused.cu).
+#ifdef RB_EXPERIMENTS
+// Geometry, tile width and tensor maps of one conv for the fused update-step kernel (experiments/update_fused.cu).
 int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
   RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
@@ -502,23 +513,28 @@ int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
   }
   return RB_OK;
 }
+#endif
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
-  if (p.kh * p.kw > 1 && !p.stat_part) {  // multi-tap convs: halo-tile kernel (each input pixel is fetched once per tap ROW, not per tap)
+#ifdef RB_EXPERIMENTS
+  if (p.kh * p.kw > 1 && !p.stat_part) {  // RAFT_B200_HALO=1: halo-tile kernel (each input pixel is fetched once per tap ROW)
     bool handled = false;
     int rc = launch_conv_halo(p, s, &handled);
     if (rc || handled) return rc;
   }
+#endif
   RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
   const int bn = choose_block_n(p.cout, m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
+#ifdef RB_EXPERIMENTS
   if (!p.stat_part) {
     bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
     int rc = launch_conv_tc2(p, s, bn, g.bw_log2, g.bh_log2, g.tiles_x, g.tiles_y, &handled);
     if (rc || handled) return rc;
   }
+#endif
   CUtensorMap maps[4];
   {
     uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
@@ -537,6 +553,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
     if ((rc = cached_tmap(&maps[2], p.w_hi, 3, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
   }
+#ifdef RB_EXPERIMENTS
   static const bool pair = getenv("RAFT_B200_PAIR") != nullptr;  // experiment: cluster-of-2 weight multicast
   if (pair && m_tiles >= 2) {
     switch (bn) {
@@ -547,6 +564,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
       default: return launch_cfg<128, true>(p, g, maps, s);
     }
   }
+#endif
   switch (bn) {
     case 16: return launch_cfg<16, false>(p, g, maps, s);
     case 32: return launch_cfg<32, false>(p, g, maps, s);

@@ -1,5 +1,6 @@
 // A1 (correlation volume + pyramid), A2/A3 (pyramid lookup), A4 (coords grid).
 // Reference: networks/model_utils.py:199-249, networks/utils.py:4-103.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -276,6 +277,210 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// A2/A3 lookup, v5 (round 2; default).  What the r01 profile said about v4: 75 SASS instructions per tap (swizzle /
+// index arithmetic), 1.86x more DRAM bytes than the algorithmic count (16-column, (2r+3)-row boxes promoted to 256-byte
+// L2 requests).  v5:
+//   * one WARP per query pixel, its 4 pyramid levels = 4 units; lane = tap (t = i*D + j, ceil(K/32) rounds), so the
+//     results of a unit are 32 consecutive words of the staging row (conflict-free) and a unit's patch is read by
+//     lanes whose rows differ by a 12-word pitch (8 distinct bank groups: conflict-free up to j = 0 / D-1);
+//   * the patch of a unit is ONE TMA box of 12 columns x (2r+2) rows fp32 starting at the UNALIGNED origin
+//     (x0, y0) = clamp(trunc(centroid - r)) -- no swizzle, 48-byte rows, L2 promotion off: per row 76 B of sectors on
+//     average instead of 80-112, and one row less.  The (2r+2)^2 footprint plus the fp32-rounding slack column fits;
+//     a unit whose rounding slack falls outside the box (trunc(fl(c+d)) == trunc(c-r)+d+1 in the last row) is detected
+//     while its index tables are built and takes a per-tap global-load path (warp-uniform branch, ~never taken);
+//   * separable index math once per unit: x table {qx, 1-qx, byte offset of x0, of x1} and y table {qy, 1-qy, row offset
+//     of y0, of y1} in shared memory (two 128-bit broadcast loads per tap), tap arithmetic exactly as the reference
+//     (trunc toward zero, clamp, weights from the CLAMPED x1/y1, add_n order, no FMA contraction) => bit-identical;
+//   * every warp is self-contained (own mbarrier, own staging row, __syncwarp only): no block-wide barrier after the
+//     prologue; the fp16 hi/lo split happens in the output pass on 8 consecutive channels per lane (128-bit stores).
+// ---------------------------------------------------------------------------------------------
+template <int R>
+struct LookupV5 {
+  static constexpr int D = 2 * R + 1, K = D * D, COLS = 12, ROWS = D + 1, PITCH = COLS * 4;
+  static constexpr int SLOT = (ROWS * PITCH + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
+  static constexpr int PB = 16, WARPS = PB, NT = WARPS * 32, ROUNDS = (K + 31) / 32;
+  static constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel (324 -> 328, 196 -> 200)
+  static constexpr int TABN = 2 * D;                // table entries per unit: D x-entries, D y-entries (float4 each)
+  static constexpr int kTabOff = PB * 4 * SLOT;
+  static constexpr int kStageOff = kTabOff + PB * 4 * TABN * 16;
+  static constexpr int kBarOff = kStageOff + PB * OUTP * 4;
+  static constexpr int kBytes = kBarOff + WARPS * 8;
+};
+struct PyramidMapsV5 {
+  CUtensorMap m[RB_NUM_LEVELS];  // (W_l, H_l, B*N) fp32, box (12, 2r+2, 1), no swizzle, no L2 promotion
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+template <int R, bool SPLIT>
+__global__ void __launch_bounds__(LookupV5<R>::NT, 3)
+corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMapsV5 maps,
+                      const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
+                      __half* __restrict__ out_lo, int out_stride, int npix) {
+  using L = LookupV5<R>;
+  constexpr int D = L::D, K = L::K;
+  extern __shared__ __align__(1024) uint8_t lk5_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pix = blockIdx.x * L::PB + warp;
+  float4* tab = reinterpret_cast<float4*>(lk5_smem + L::kTabOff) + warp * 4 * L::TABN;
+  float* stage = reinterpret_cast<float*>(lk5_smem + L::kStageOff) + warp * L::OUTP;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lk5_smem + L::kBarOff) + warp;
+  uint8_t* patch = lk5_smem + warp * 4 * L::SLOT;
+  const uint32_t patch_u32 = tc::smem_u32(patch);
+  const bool live = pix < npix;
+
+  int n_tma = 0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) n_tma += pv.tma_ok[l] ? 1 : 0;
+  if (lane == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async();
+    if (n_tma && live) tc::mbar_arrive_expect_tx(bar, (uint32_t)(n_tma * L::ROWS * L::PITCH));
+  }
+  if (lane < L::OUTP - 4 * K) stage[4 * K + lane] = 0.f;  // channel padding of the staged row
+  // taps of this lane: t = lane + 32*round = i*D + j   (i walks x, j walks y: model_utils.py:235-237)
+  int ti[L::ROUNDS], tj[L::ROUNDS];
+#pragma unroll
+  for (int rd = 0; rd < L::ROUNDS; ++rd) {
+    const int t = lane + 32 * rd;
+    ti[rd] = t / D;
+    tj[rd] = t - ti[rd] * D;
+  }
+  __syncwarp();
+  // PDL: dependents may be scheduled from here on (their own griddepcontrol.wait still waits for this grid to finish);
+  // nothing above touched global memory, everything below comes after the predecessor kernel.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!live) return;  // warp-uniform; no block-wide barrier below
+
+  const float2 c = __ldg(coords + pix);
+  // ---- unit origins (lanes 0..3 hold the values of unit k = lane) and TMA issue ----------------------------------------
+  int bx, by;
+  {
+    const int k = lane & 3;
+    const float inv = 1.0f / (float)(1 << k);  // centroid / 2**i (model_utils.py:239), exact
+    const int H = pv.hl[k], W = pv.wl[k];
+    bx = min(max((int)__fadd_rn(c.x * inv, (float)(-R)), 0), W - 1);
+    by = min(max((int)__fadd_rn(c.y * inv, (float)(-R)), 0), H - 1);
+    if (lane < 4 && pv.tma_ok[k]) tc::tma_load_3d(&maps.m[k], bar, patch + k * L::SLOT, bx, by, pix);
+  }
+  // ---- index tables: lane -> (unit k = lane >> 3, entry e = lane & 7); entry 8 (r = 4) by the lanes with e = 0 / 1 ------
+  unsigned bad = 0;
+  {
+    const int k = lane >> 3, e = lane & 7;
+    const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
+    const float inv = 1.0f / (float)(1 << k);
+    const float cx = c.x * inv, cy = c.y * inv;
+    const int H = pv.hl[k], W = pv.wl[k];
+    auto x_entry = [&](int i) {
+      const float x = __fadd_rn(cx, (float)(i - R));
+      int x0 = (int)x;  // tf.cast truncates toward zero (utils.py:54-57)
+      int x1 = x0 + 1;
+      x0 = min(max(x0, 0), W - 1);
+      x1 = min(max(x1, 0), W - 1);
+      const float qx = __fsub_rn((float)x1, x);  // utils.py:84 (clamped x1)
+      const int a0 = x0 - bxk, a1 = x1 - bxk;
+      if ((unsigned)a0 >= (unsigned)L::COLS || (unsigned)a1 >= (unsigned)L::COLS) bad = 1;
+      tab[k * L::TABN + i] = make_float4(qx, __fsub_rn(1.0f, qx), __int_as_float(a0 * 4), __int_as_float(a1 * 4));
+    };
+    auto y_entry = [&](int j) {
+      const float y = __fadd_rn(cy, (float)(j - R));
+      int y0 = (int)y;
+      int y1 = y0 + 1;
+      y0 = min(max(y0, 0), H - 1);
+      y1 = min(max(y1, 0), H - 1);
+      const float qy = __fsub_rn((float)y1, y);  // utils.py:85
+      const int r0 = y0 - byk, r1 = y1 - byk;
+      if ((unsigned)r0 >= (unsigned)L::ROWS || (unsigned)r1 >= (unsigned)L::ROWS) bad = 1;
+      tab[k * L::TABN + D + j] = make_float4(qy, __fsub_rn(1.0f, qy), __int_as_float(r0 * L::PITCH), __int_as_float(r1 * L::PITCH));
+    };
+    if (e < D) { x_entry(e); y_entry(e); }
+    if (D > 8) {
+      if (e == 0) x_entry(8);
+      if (e == 1) y_entry(8);
+    }
+  }
+  const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);  // bits 8k..8k+7 belong to unit k
+  // ---- levels TMA cannot address (W % 4 != 0): plain loads into the same layout ------------------------------------------
+  if (n_tma < 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (pv.tma_ok[k]) continue;
+      const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
+      const int H = pv.hl[k], W = pv.wl[k];
+      for (int e = lane; e < L::ROWS * 3; e += 32) {
+        const int row = e / 3, ch = e - row * 3;
+        const float* src = pv.base[k] + ((size_t)pix * H + min(byk + row, H - 1)) * W;
+        const int col = bxk + ch * 4;
+        float4 v;
+        v.x = __ldg(src + min(col + 0, W - 1)); v.y = __ldg(src + min(col + 1, W - 1));
+        v.z = __ldg(src + min(col + 2, W - 1)); v.w = __ldg(src + min(col + 3, W - 1));
+        *reinterpret_cast<float4*>(patch + k * L::SLOT + row * L::PITCH + ch * 16) = v;
+      }
+    }
+  }
+  __syncwarp();  // tables and fallback patches visible to the warp
+  if (n_tma) {
+    if (lane == 0) tc::mbar_wait(bar, 0);  // one polling lane ...
+    __syncwarp();
+    tc::mbar_wait(bar, 0);                 // ... then every lane observes the completed phase (returns at once)
+  }
+  // ---- taps -----------------------------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4* xt = tab + k * L::TABN;
+    const float4* yt = xt + D;
+    const uint32_t pb = patch_u32 + k * L::SLOT;
+    const bool slow = ((badmask >> (8 * k)) & 0xffu) != 0;  // warp-uniform
+#pragma unroll
+    for (int rd = 0; rd < L::ROUNDS; ++rd) {
+      const int t = lane + 32 * rd;
+      if (t < K) {
+        const float4 X = xt[ti[rd]], Y = yt[tj[rd]];
+        const float wa = __fmul_rn(X.x, Y.x), wb = __fmul_rn(X.x, Y.y);  // utils.py:86-89
+        const float wc = __fmul_rn(X.y, Y.x), wd = __fmul_rn(X.y, Y.y);
+        const int a0 = __float_as_int(X.z), a1 = __float_as_int(X.w), r0 = __float_as_int(Y.z), r1 = __float_as_int(Y.w);
+        float Ia, Ib, Ic, Id;
+        if (!slow) {
+          Ia = lds_f32(pb + r0 + a0); Ib = lds_f32(pb + r1 + a0);
+          Ic = lds_f32(pb + r0 + a1); Id = lds_f32(pb + r1 + a1);
+        } else {  // rounding slack outside the box: read the four texels from the volume itself
+          const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
+          const int H = pv.hl[k], W = pv.wl[k];
+          const float* img = pv.base[k] + (size_t)pix * H * W;
+          const int x0 = bxk + (a0 >> 2), x1 = bxk + (a1 >> 2), y0 = byk + r0 / L::PITCH, y1 = byk + r1 / L::PITCH;
+          Ia = __ldg(img + (size_t)y0 * W + x0); Ib = __ldg(img + (size_t)y1 * W + x0);
+          Ic = __ldg(img + (size_t)y0 * W + x1); Id = __ldg(img + (size_t)y1 * W + x1);
+        }
+        stage[k * K + t] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
+                                     __fmul_rn(wd, Id));  // tf.add_n order (utils.py:98)
+      }
+    }
+  }
+  __syncwarp();
+  // ---- output pass: this warp's pixel, 8 consecutive channels per lane --------------------------------------------------------
+  if constexpr (SPLIT) {
+    for (int g = lane; g < L::OUTP / 8; g += 32) {
+      const float4 v0 = *reinterpret_cast<const float4*>(stage + g * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(stage + g * 8 + 4);
+      uint4 h, l;
+      split2(v0.x, v0.y, h.x, l.x); split2(v0.z, v0.w, h.y, l.y);
+      split2(v1.x, v1.y, h.z, l.z); split2(v1.z, v1.w, h.w, l.w);
+      *reinterpret_cast<uint4*>(out_hi + (size_t)pix * out_stride + g * 8) = h;
+      *reinterpret_cast<uint4*>(out_lo + (size_t)pix * out_stride + g * 8) = l;
+    }
+  } else {
+    for (int g = lane; g < K; g += 32)  // 4*K floats = K float4 (out_stride = 4*K, 16-byte aligned rows)
+      *reinterpret_cast<float4*>(out_f32 + (size_t)pix * out_stride + g * 4) = *reinterpret_cast<const float4*>(stage + g * 4);
+  }
+}
+
 // General form of bilinear_sampler / tf_grid_sample (utils.py:39-103) for single-channel images:
 // img [n,H,W,1], coords [n,S,2] -> out [n,S].  One thread per sample; same arithmetic as above.
 __global__ void bilinear_sample_kernel(const float* __restrict__ img, const float2* __restrict__ coords,
@@ -323,11 +528,13 @@ static size_t lookup_smem_bytes() {
 template <int R, bool SPLIT>
 static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, const float2* c2, float* out_f32, __half* out_hi,
                              __half* out_lo, int out_stride, int npix, cudaStream_t s) {
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   const size_t smem = lookup_smem_bytes<R>();
-  if (!attr_set) {
+  int dev = 0, rc_dev;
+  if ((rc_dev = current_device(&dev))) return rc_dev;
+  if (!attr_set.test(dev)) {
     RB_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<R, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.set(dev);
   }
   dim3 grid((npix + kLookupPB - 1) / kLookupPB), block(kLookupPB * 4 * (2 * R + 1));
   // Programmatic dependent launch (as the convs, conv_tc.cu): inside the iteration loop the lookup follows the flow-head
@@ -350,6 +557,34 @@ static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, con
   return RB_OK;
 }
 
+template <int R, bool SPLIT>
+static int launch_lookup_v5(const PyramidView& pv, const PyramidMapsV5& maps, const float2* c2, float* out_f32, __half* out_hi,
+                            __half* out_lo, int out_stride, int npix, cudaStream_t s) {
+  using L = LookupV5<R>;
+  static PerDeviceOnce attr_set;
+  int dev = 0, rc_dev;
+  if ((rc_dev = current_device(&dev))) return rc_dev;
+  if (!attr_set.test(dev)) {
+    RB_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_v5_kernel<R, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+    attr_set.set(dev);
+  }
+  static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((npix + L::PB - 1) / L::PB);
+  cfg.blockDim = dim3(L::NT);
+  cfg.dynamicSmemBytes = L::kBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl;
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_v5_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix));
+  RB_CHECK_LAUNCH("corr_lookup_v5_kernel");
+  return RB_OK;
+}
+
 int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
                   __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s) {
   PyramidView pv;
@@ -359,6 +594,26 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
   RB_REQUIRE(out_hi == nullptr || out_stride % 8 == 0, RB_ERR_BAD_SHAPE, "lookup: split output stride %d not a multiple of 8",
              out_stride);
   const int npix = B * h * w;
+  const float2* c2 = reinterpret_cast<const float2*>(coords);
+  const bool split = out_hi != nullptr;
+  static const bool v4 = getenv("RAFT_B200_LOOKUP_V4") != nullptr;  // A/B: the round-1 kernel (16-column swizzled boxes)
+  const bool f32_rows_ok = split || (out_stride % 4 == 0 && reinterpret_cast<uintptr_t>(out_f32) % 16 == 0);
+  if (!v4 && f32_rows_ok) {
+    PyramidMapsV5 maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int l = 0; l < RB_NUM_LEVELS; ++l) {
+      if (!pv.tma_ok[l]) continue;
+      uint64_t dims[3] = {(uint64_t)pv.wl[l], (uint64_t)pv.hl[l], (uint64_t)npix};
+      uint64_t str[2] = {(uint64_t)pv.wl[l] * 4, (uint64_t)pv.wl[l] * pv.hl[l] * 4};
+      uint32_t box[3] = {12u, (uint32_t)(2 * radius + 2), 1};
+      if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_PLAIN) != RB_OK) pv.tma_ok[l] = 0;  // plain loads
+    }
+    if (radius == 4)
+      return split ? launch_lookup_v5<4, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
+                   : launch_lookup_v5<4, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
+    return split ? launch_lookup_v5<3, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
+                 : launch_lookup_v5<3, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
+  }
   PyramidMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int l = 0; l < RB_NUM_LEVELS; ++l) {
@@ -368,8 +623,6 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
     uint32_t box[3] = {(uint32_t)kPatchCols, (uint32_t)(2 * radius + 3), 1};
     if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_SW64) != RB_OK) pv.tma_ok[l] = 0;  // plain loads instead
   }
-  const float2* c2 = reinterpret_cast<const float2*>(coords);
-  const bool split = out_hi != nullptr;
   if (radius == 4)
     return split ? launch_lookup_cfg<4, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
                  : launch_lookup_cfg<4, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);

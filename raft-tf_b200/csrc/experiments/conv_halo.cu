@@ -18,7 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "tc_common.cuh"
+#include "../tc_common.cuh"
 
 namespace rb {
 using namespace tc;
@@ -266,10 +266,12 @@ static int halo_block_n(int cout, long m_tiles) {
 template <int BLOCK_N>
 static int launch_halo_cfg(const ConvParams& p, const HaloGeom& g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = HaloCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  int dev = 0, rc_dev;
+  if ((rc_dev = current_device(&dev))) return rc_dev;
+  if (!attr_set.test(dev)) {
     RB_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.set(dev);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -15,7 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "tc_common.cuh"
+#include "../tc_common.cuh"
 
 namespace rb {
 using namespace tc;
@@ -198,15 +198,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 template <int BLOCK_N>
 static int launch_tc2_cfg(const ConvParams& p, Tile2Geom g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = Tc2Cfg<BLOCK_N>;
-  static bool attr_set = false;
-  static int num_sms = 148;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  int dev = 0, rc_dev;
+  if ((rc_dev = current_device(&dev))) return rc_dev;
+  if (!attr_set.test(dev)) {
     RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    int dev = 0;
-    RB_CHECK_CUDA(cudaGetDevice(&dev));
-    RB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true;
+    attr_set.set(dev);
   }
+  const int num_sms = device_sm_count(dev);
   g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
   g.m_tiles = p.B * g.tiles_x * g.tiles_y;
   g.total_pairs = ((g.m_tiles + 1) / 2) * g.n_tiles;

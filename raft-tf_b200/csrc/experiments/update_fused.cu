@@ -18,7 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "tc_common.cuh"
+#include "../tc_common.cuh"
 
 namespace rb {
 using namespace tc;
@@ -276,15 +276,14 @@ __global__ void __launch_bounds__(kFThreads, 1) fused_conv_kernel(const __grid_c
 }
 
 int launch_fused_jobs(const FusedJobs& jobs, cudaStream_t s) {
-  static bool attr_set = false;
-  static int num_sms = 148;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  int dev = 0, rc_dev;
+  if ((rc_dev = current_device(&dev))) return rc_dev;
+  if (!attr_set.test(dev)) {
     RB_CHECK_CUDA(cudaFuncSetAttribute(fused_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
-    int dev = 0;
-    RB_CHECK_CUDA(cudaGetDevice(&dev));
-    RB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true;
+    attr_set.set(dev);
   }
+  const int num_sms = device_sm_count(dev);
   RB_REQUIRE(jobs.n > 0 && jobs.n <= kMaxFusedJobs && jobs.counters, RB_ERR_BAD_ARG, "fused update: bad job list");
   int max_tiles = 0;
   for (int j = 0; j < jobs.n; ++j) {

@@ -189,7 +189,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* a, uint32_t* b) {
 
 // ---- host: tensor maps --------------------------------------------------------------------------------
 // up to 4 dims (innermost first), zero fill for out-of-bounds boxes; kind selects element type and swizzle
-enum { TMAP_F16_SW128 = 0, TMAP_F32_SW64 = 1 };
+enum { TMAP_F16_SW128 = 0, TMAP_F32_SW64 = 1, TMAP_F32_PLAIN = 2 };  // PLAIN: fp32, no swizzle, no L2 promotion (lookup v5)
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int kind);
 
@@ -203,7 +203,8 @@ struct TileGeom {
   int total_tiles;       // work items: m_tiles * n_tiles, or ceil(m_tiles/2) * n_tiles PAIRS in cluster mode
 };
 
-// One conv of the fused update-step kernel (update_fused.cu)
+#ifdef RB_EXPERIMENTS
+// One conv of the fused update-step kernel (experiments/update_fused.cu)
 struct FusedJob {
   CUtensorMap m[4];  // A_hi, A_lo, B_hi, B_lo
   ConvParams p;
@@ -225,6 +226,7 @@ struct FusedJobs {
                            // 2 no A_lo load, 4 no B loads, 8 no A_hi load, 16 no MMAs at all, 32 no epilogue stores
 };
 int launch_fused_jobs(const FusedJobs& jobs, cudaStream_t s);
+#endif
 
 // per-thread cache of encoded tensor maps (conv_tc.cu)
 int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,

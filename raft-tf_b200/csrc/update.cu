@@ -451,16 +451,21 @@ static int launch_flow_head2(const ConvParams& p, cudaStream_t s) {
 // step record 8 timestamps per CTA for each of its convs, in launch order, 4096 CTAs per conv.
 static thread_local long long* g_dbg = nullptr;
 static thread_local int g_dbg_idx = 0;
-// Fused mode (RAFT_B200_FUSED=1): the convs of one update step are recorded into a job list and run as ONE
-// persistent kernel with grid barriers between dependent convs (update_fused.cu).
+#ifdef RB_EXPERIMENTS
+// Fused mode (experiment build only, RAFT_B200_FUSED=1): the convs of one update step are recorded into a job list and
+// run as ONE persistent kernel with grid barriers between dependent convs (experiments/update_fused.cu).
 static thread_local FusedJobs* g_rec = nullptr;
 static thread_local int g_rec_wait = 1, g_rec_offset = 0;
 static inline bool fused_mode() {
   static const bool on = getenv("RAFT_B200_FUSED") != nullptr;
   return on && math_mode() == RB_MATH_TC;
 }
+#else
+static inline constexpr bool fused_mode() { return false; }
+#endif
 static int launch_conv_dbg(ConvParams& p, cudaStream_t s) {
   static const int early = getenv("RAFT_B200_PDL_EARLY") ? 1 : 0;
+#ifdef RB_EXPERIMENTS
   if (g_rec) {
     RB_REQUIRE(g_rec->n < kMaxFusedJobs, RB_ERR_UNSUPPORTED, "fused update: too many convs");
     FusedJob& jb = g_rec->job[g_rec->n];
@@ -472,6 +477,7 @@ static int launch_conv_dbg(ConvParams& p, cudaStream_t s) {
     g_rec->n++;
     return RB_OK;
   }
+#endif
   p.pdl_early = early;
   if (g_dbg) p.dbg = g_dbg + (size_t)(g_dbg_idx++) * 4096 * 8;
   return launch_conv(p, s);
@@ -516,8 +522,9 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   const int foff = xoff + v.mo_out;       // channel offset of the raw flow
   int rc;
   g_dbg_idx = 0;
-  FusedJobs jobs;
   const bool fused = fused_mode();
+#ifdef RB_EXPERIMENTS
+  FusedJobs jobs;
   if (fused) {
     static const int whatif = getenv("RAFT_B200_WHATIF") ? atoi(getenv("RAFT_B200_WHATIF")) : 0;
     jobs.n = 0; jobs.counters = W.counters; jobs.whatif = whatif; jobs.dbg = g_dbg;
@@ -527,6 +534,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   struct RecGuard {  // recording never outlives this call, whatever the exit path
     ~RecGuard() { g_rec = nullptr; }
   } rec_guard;
+#endif
   // ---- motion encoder (model_utils.py:110-129) ----
   SideStream* ss;
   if ((rc = side_stream(&ss))) return rc;
@@ -562,6 +570,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   if (pyramid) {
     if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s))) return rc;
   }
+#ifdef RB_EXPERIMENTS
   if (fused) {
     // both branches (flow_conv7 on the side stream, the lookup here) end before the fused kernel starts; its first two
     // jobs (convc1, convf2) are independent of each other and are spread over different CTAs
@@ -579,11 +588,15 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     g_rec_wait = 1;
     return r;
   };
+#else
+  auto record_convf2 = []() -> int { return RB_OK; };
+#endif
   if (!v.small) {
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
     set_act(p, ACT_RELU, W.c1, v.c1, 0);
     if ((rc = launch_conv_dbg(p, s))) return rc;
-    if ((rc = record_convf2())) return rc;
+    rc = record_convf2();
+    if (rc) return rc;
     p = base_params(v, L, blob, P_CONVC2, W.c1, v.c1, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
     if ((rc = launch_conv_dbg(p, s))) return rc;
@@ -591,7 +604,8 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     ConvParams p = base_params(v, L, blob, P_CONVC1, W.corr, v.corr_pad, 0, B, h, w);
     set_act(p, ACT_RELU, W.cf, v.cf, 0);
     if ((rc = launch_conv_dbg(p, s))) return rc;
-    if ((rc = record_convf2())) return rc;
+    rc = record_convf2();
+    if (rc) return rc;
   }
   if (!fused) RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
   {
@@ -649,10 +663,12 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     p.epi = EPI_F32; p.f0 = mask_out; p.scale = 0.25f;
     if ((rc = launch_conv_dbg(p, s))) return rc;
   }
+#ifdef RB_EXPERIMENTS
   if (fused) {
     g_rec = nullptr;
     if ((rc = launch_fused_jobs(jobs, s))) return rc;
   }
+#endif
   return RB_OK;
 }
 

@@ -7,9 +7,12 @@ namespace rb {
 // Convex 8x upsampling.  One thread per fine pixel (sy,sx) of a coarse pixel; 4 coarse pixels per
 // block.  mask channel = k*64 + sy*8 + sx with k = ky*3+kx (RAFT.py:125); softmax over k (:126);
 // 3x3 zero-padded patches of 8*flow (:128); weighted sum over k (:131).
+// The output may be a CROP of the 8h x 8w field: out is [B,oH,oW,2] and holds rows [top, top+oH) x cols [left, left+oW)
+// (frames that were replicate-padded to a multiple of 8 are cropped back here, not by a torch slice afterwards).
 __global__ void __launch_bounds__(256) upsample_convex_kernel(const float2* __restrict__ coords1,
                                                               const float* __restrict__ mask,
-                                                              float2* __restrict__ out, int B, int h, int w) {
+                                                              float2* __restrict__ out, int B, int h, int w, int top,
+                                                              int left, int oH, int oW) {
   const int cp = blockIdx.x * 4 + (threadIdx.x >> 6);
   const int t = threadIdx.x & 63;
   if (cp >= B * h * w) return;
@@ -36,18 +39,18 @@ __global__ void __launch_bounds__(256) upsample_convex_kernel(const float2* __re
     ax += fx * p;
     ay += fy * p;
   }
-  const int sy = t >> 3, sx = t & 7;
-  out[((size_t)(b * h * 8) + (y * 8 + sy)) * (w * 8) + x * 8 + sx] = make_float2(ax, ay);
+  const int oy = y * 8 + (t >> 3) - top, ox = x * 8 + (t & 7) - left;
+  if (oy >= 0 && oy < oH && ox >= 0 && ox < oW) out[((size_t)b * oH + oy) * oW + ox] = make_float2(ax, ay);
 }
 
 // tf.image.resize_bilinear(flow, 8x, align_corners=True) -- and no x8 of the values unless
 // scale says so (reference quirk, utils.py:110).
 __global__ void upflow8_kernel(const float2* __restrict__ coords1, float2* __restrict__ out, int B, int h, int w,
-                               float scale) {
+                               float scale, int top, int left, int oH, int oW) {
   const int H = 8 * h, Wd = 8 * w;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * H * Wd) return;
-  const int ox = i % Wd, oy = (i / Wd) % H, b = i / ((size_t)Wd * H);
+  if (i >= (size_t)B * oH * oW) return;
+  const int ox = (int)(i % oW) + left, oy = (int)((i / oW) % oH) + top, b = (int)(i / ((size_t)oW * oH));
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = Wd > 1 ? (float)(w - 1) / (float)(Wd - 1) : 0.f;
   const float fy = (float)oy * sy, fx = (float)ox * sx;
@@ -68,23 +71,43 @@ __global__ void upflow8_kernel(const float2* __restrict__ coords1, float2* __res
 
 using namespace rb;
 
-extern "C" int rb_upsample_convex(const float* coords1, const float* mask, float* out, int B, int h, int w,
-                                  void* stream) {
+static int check_crop(const char* fn, int h, int w, int top, int left, int oH, int oW) {
+  RB_REQUIRE(top >= 0 && left >= 0 && oH > 0 && oW > 0 && top + oH <= 8 * h && left + oW <= 8 * w, RB_ERR_BAD_SHAPE,
+             "%s: crop rows [%d,%d) cols [%d,%d) outside the %dx%d field", fn, top, top + oH, left, left + oW, 8 * h, 8 * w);
+  return RB_OK;
+}
+
+extern "C" int rb_upsample_convex_crop(const float* coords1, const float* mask, float* out, int B, int h, int w, int top,
+                                       int left, int out_h, int out_w, void* stream) {
   RB_REQUIRE(coords1 && mask && out, RB_ERR_BAD_ARG, "rb_upsample_convex: null pointer");
   RB_REQUIRE(B > 0 && h > 0 && w > 0, RB_ERR_BAD_SHAPE, "rb_upsample_convex: bad shape");
+  int rc = check_crop("rb_upsample_convex_crop", h, w, top, left, out_h, out_w);
+  if (rc) return rc;
   int n = B * h * w;
   upsample_convex_kernel<<<(n + 3) / 4, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2*>(coords1), mask, reinterpret_cast<float2*>(out), B, h, w);
+      reinterpret_cast<const float2*>(coords1), mask, reinterpret_cast<float2*>(out), B, h, w, top, left, out_h, out_w);
   RB_CHECK_LAUNCH("upsample_convex_kernel");
   return RB_OK;
 }
 
-extern "C" int rb_upflow8(const float* coords1, float* out, int B, int h, int w, float scale, void* stream) {
+extern "C" int rb_upsample_convex(const float* coords1, const float* mask, float* out, int B, int h, int w,
+                                  void* stream) {
+  return rb_upsample_convex_crop(coords1, mask, out, B, h, w, 0, 0, 8 * h, 8 * w, stream);
+}
+
+extern "C" int rb_upflow8_crop(const float* coords1, float* out, int B, int h, int w, float scale, int top, int left,
+                               int out_h, int out_w, void* stream) {
   RB_REQUIRE(coords1 && out, RB_ERR_BAD_ARG, "rb_upflow8: null pointer");
   RB_REQUIRE(B > 0 && h > 0 && w > 0, RB_ERR_BAD_SHAPE, "rb_upflow8: bad shape");
-  size_t n = (size_t)B * h * w * 64;
+  int rc = check_crop("rb_upflow8_crop", h, w, top, left, out_h, out_w);
+  if (rc) return rc;
+  size_t n = (size_t)B * out_h * out_w;
   upflow8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float2*>(coords1), reinterpret_cast<float2*>(out), B, h, w, scale);
+      reinterpret_cast<const float2*>(coords1), reinterpret_cast<float2*>(out), B, h, w, scale, top, left, out_h, out_w);
   RB_CHECK_LAUNCH("upflow8_kernel");
   return RB_OK;
+}
+
+extern "C" int rb_upflow8(const float* coords1, float* out, int B, int h, int w, float scale, void* stream) {
+  return rb_upflow8_crop(coords1, out, B, h, w, scale, 0, 0, 8 * h, 8 * w, stream);
 }

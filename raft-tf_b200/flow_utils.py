@@ -22,24 +22,31 @@ def make_colorwheel():
 
 
 def flow_to_color(flow_uv, clip_flow=None, convert_to_bgr=False):
+    """[H,W,2] flow -> [H,W,3] uint8 colour image.  Pinned bit for bit against the reference function run in-process
+    (oracle/make_flowcolor_golden.py -> tests/golden/flow_to_color.npz), which fixes the floating-point TYPE of every
+    step for float32 flows (flow_utils.py:58-121): direction / radius in the flow's dtype, interpolation weight and
+    colours in float64, floor(255*col) quantisation."""
+    flow_uv = np.asarray(flow_uv)
     assert flow_uv.ndim == 3 and flow_uv.shape[2] == 2
     if clip_flow is not None:
         flow_uv = np.clip(flow_uv, 0, clip_flow)
-    u, v = flow_uv[..., 0].astype(np.float64), flow_uv[..., 1].astype(np.float64)
-    rmax = np.sqrt(u * u + v * v).max()
-    u, v = u / (rmax + 1e-5), v / (rmax + 1e-5)
+    u, v = flow_uv[..., 0], flow_uv[..., 1]
+    ft = u.dtype if u.dtype.kind == "f" else np.dtype(np.float64)
+    rad = np.sqrt(np.square(u) + np.square(v))
+    den = (rad.max() + np.asarray(1e-5, dtype=ft)).astype(ft)  # rad_max + epsilon in the flow's precision
+    u, v = (u / den).astype(ft), (v / den).astype(ft)
     wheel = make_colorwheel()
     n = wheel.shape[0]
-    rad = np.sqrt(u * u + v * v)
-    fk = (np.arctan2(-v, -u) / np.pi + 1) / 2 * (n - 1) + 1
+    rad = np.sqrt(np.square(u) + np.square(v))
+    fk = ((np.arctan2(-v, -u) / np.asarray(np.pi, dtype=ft)).astype(ft) + 1) / 2 * (n - 1) + 1
     k0 = np.minimum(np.floor(fk).astype(np.int32), n - 2)
     k1 = k0 + 1
     k1[k1 == n] = 1
-    f = fk - k0
+    f = fk.astype(np.float64) - k0  # float64 from here on, like (float32 array - int32 array) in numpy
+    inside = rad <= 1
     img = np.zeros(u.shape + (3,), np.uint8)
     for ch in range(3):
-        col = (1 - f) * wheel[k0, ch] / 255.0 + f * wheel[k1, ch] / 255.0
-        inside = rad <= 1
+        col = (1 - f) * (wheel[k0, ch] / 255.0) + f * (wheel[k1, ch] / 255.0)
         col = np.where(inside, 1 - rad * (1 - col), col * 0.75)
         img[..., 2 - ch if convert_to_bgr else ch] = np.floor(255 * col)
     return img

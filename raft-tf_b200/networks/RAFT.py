@@ -84,16 +84,12 @@ class RAFT(object):
     # -- inference ---------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, input_left, input_right):
-        """[B,H,W,3] in [0,1] (numpy or torch, BGR like the reference) -> [B,H,W,2] torch CUDA flow."""
-        l = torch.as_tensor(input_left, dtype=torch.float32).to(self.device, non_blocking=True)
-        r = torch.as_tensor(input_right, dtype=torch.float32).to(self.device, non_blocking=True)
-        B, H, W, _ = l.shape
-        ph, pw = (-H) % 8, (-W) % 8
-        if ph or pw:  # upstream InputPadder 'sintel' convention: split the pad on both sides
-            pad = (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)
-            l = torch.nn.functional.pad(l.permute(0, 3, 1, 2), pad, mode='replicate').permute(0, 2, 3, 1).contiguous()
-            r = torch.nn.functional.pad(r.permute(0, 3, 1, 2), pad, mode='replicate').permute(0, 2, 3, 1).contiguous()
-        flow = self.engine().forward(l, r)
-        if ph or pw:
-            flow = flow[:, ph // 2:ph // 2 + H, pw // 2:pw // 2 + W, :]
-        return flow
+        """[B,H,W,3] frames, BGR like the reference -- fp32 in [0,1] (the reference's placeholders, RAFT.py:45-51) or
+        uint8 in [0,255] (extension: the /255 of test_dataflow.py:96-97 then runs on the GPU); numpy or torch, host or
+        CUDA -> [B,H,W,2] torch CUDA flow (a fresh tensor per call, like a session.run result).  H, W that are not
+        multiples of 8 are replicate-padded and the flow cropped back, both inside the engine's own kernels."""
+        def as_tensor(x):
+            t = torch.as_tensor(x)
+            return t if t.dtype == torch.uint8 else t.to(torch.float32)
+        flow = self.engine().forward(as_tensor(input_left), as_tensor(input_right))
+        return flow.clone()

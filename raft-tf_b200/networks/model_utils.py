@@ -8,13 +8,19 @@ import torch
 from raft_b200 import capi
 from raft_b200.weights import pack_update_block
 
-_VARS = {"params": None, "blobs": {}}
+_VARS = {"params": None, "blobs": {}, "generation": 0}
+_ENC = {}  # packed encoders of the current checkpoint, see _encoder()
 
 
 def set_variables(params):
-    """params: dict of reference variable names -> numpy arrays (the .npz content)."""
+    """params: dict of reference variable names -> numpy arrays (the .npz content).
+
+    The functional API below (GetCorrPyramid ... SmallEncoder) is module-level like the reference's TF variable
+    scopes; loading another checkpoint drops every packed blob / encoder of the previous one."""
     _VARS["params"] = params
     _VARS["blobs"] = {}
+    _VARS["generation"] += 1  # cache key of the packed encoders (id() of a dead dict can be reused)
+    _ENC.clear()
 
 
 def _blob(small, device):
@@ -116,12 +122,11 @@ def SmallUpdateBlock(net, inp, corr, flow, name="update_block", hidden_dim=96):
 
 
 # ---- encoders (model_utils.py:61-105) -----------------------------------------------------------
-_ENC = {}
 
 
 def _encoder(name, small, norm_fn, out_dim, device):
     from raft_b200.encoders import CudaEncoder
-    key = (name, bool(small), norm_fn, int(out_dim), str(device), id(_VARS["params"]))
+    key = (name, bool(small), norm_fn, int(out_dim), str(device), _VARS["generation"])
     if key not in _ENC:
         if _VARS["params"] is None:
             raise RuntimeError("networks.model_utils.set_variables(params) has not been called")

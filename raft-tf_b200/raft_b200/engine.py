@@ -1,8 +1,9 @@
 """Host-side orchestration of one RAFT forward pass on one GPU.
 
-encoders (torch/cuDNN, out of scope this round) -> rb_corr_build -> rb_update_set_state ->
-rb_raft_iterate (lookup + update block per iteration; optionally replayed from a CUDA graph) ->
-rb_upsample_convex / rb_upflow8.  Mirrors RAFT.network_graph (networks/RAFT.py:78-109).
+rb_encoder_forward x2 (fnet on both frames, cnet on a forked stream; csrc/encoder.cu) -> rb_corr_build ->
+rb_update_set_state_cnet -> rb_raft_iterate (lookup + update block per iteration) -> rb_upsample_convex /
+rb_upflow8, all replayed from ONE CUDA graph.  Mirrors RAFT.network_graph (networks/RAFT.py:78-109).
+The torch/cuDNN restatement of the encoders (encoders.Encoder) is a cross-check behind RAFT_B200_TORCH_ENCODERS=1.
 """
 from __future__ import annotations
 
@@ -27,8 +28,7 @@ class RaftEngine:
         self.hidden, self.ctx, self.radius, self.fdim = (96, 64, 3, 128) if small else (128, 128, 4, 256)
         self.use_graph = use_graph and not os.environ.get("RAFT_B200_NO_GRAPH")
         self.math_mode = math_mode
-        torch.backends.cudnn.allow_tf32 = False  # the reference is fp32 end to end
-        torch.backends.cudnn.benchmark = True  # encoders (cuDNN, out of scope): let it pick its best fp32 kernels
+        torch.backends.cudnn.allow_tf32 = False  # the reference is fp32 end to end (only matters for the cuDNN cross-check)
         torch.backends.cuda.matmul.allow_tf32 = False
         # encoders: raft_b200's own kernels by default; RAFT_B200_TORCH_ENCODERS=1 selects the torch/cuDNN restatement
         self.torch_encoders = bool(os.environ.get("RAFT_B200_TORCH_ENCODERS"))
@@ -45,18 +45,22 @@ class RaftEngine:
         self._graph = None
         self._enc_stream = None   # forked stream of the context encoder (encode())
         self._cnet_pending = False
+        self._range_checked = False  # first forward of this weight set: fp16-range check of the split path's inputs
 
     # ---- buffers -------------------------------------------------------------------------------
-    def _ensure(self, B: int, H: int, W: int):
-        if self._shape == (B, H, W):
+    def _ensure(self, B: int, H: int, W: int, u8: bool = False):
+        """Buffers for B frame pairs of H x W pixels.  H, W need not be multiples of 8: frames are replicate-padded
+        to (Hp, Wp) by rb_frames_prepare (upstream InputPadder 'sintel' split) and the flow is cropped
+        back by the upsampling kernel -- the reference itself cannot run such shapes."""
+        if self._shape == (B, H, W, u8):
             return
-        if H % 8 or W % 8:
-            raise ValueError(f"H and W must be multiples of 8 (got {H}x{W}); the reference has the same constraint "
-                             "(SURVEY fact 6) -- pad first, see networks.RAFT")
-        h, w, s = H // 8, W // 8, int(self.small)
+        ph, pw = (-H) % 8, (-W) % 8
+        self.pad = (ph // 2, ph - ph // 2, pw // 2, pw - pw // 2)  # top, bottom, left, right
+        Hp, Wp = H + ph, W + pw
+        h, w, s = Hp // 8, Wp // 8, int(self.small)
         d = self.device
         lib = capi.lib
-        self.h, self.w = h, w
+        self.h, self.w, self.Hp, self.Wp = h, w, Hp, Wp
         self.pyr_bytes = capi.size_query(lib.rb_corr_pyramid_bytes, B, h, w)
         self.pyramid = torch.empty(self.pyr_bytes // 4, dtype=torch.float32, device=d)
         self.cws_bytes = capi.size_query(lib.rb_corr_workspace_bytes, B, h, w, self.fdim)
@@ -69,8 +73,12 @@ class RaftEngine:
         self.fmaps = torch.empty(2 * B, h, w, self.fdim, dtype=torch.float32, device=d)
         self.fmap1, self.fmap2 = self.fmaps[:B], self.fmaps[B:]
         self.cmap = torch.empty(B, h, w, self.hidden + self.ctx, dtype=torch.float32, device=d)
-        self.images = torch.empty(2 * B, H, W, 3, dtype=torch.float32, device=d)  # [left | right], [0,1]
-        self._shape = (B, H, W)
+        self.images = torch.empty(2 * B, Hp, Wp, 3, dtype=torch.float32, device=d)  # [left | right], [0,1], padded
+        # staging buffer of the raw frames (uint8 or unpadded fp32); fp32 frames that need no padding go straight
+        # into self.images
+        self.staged = bool(u8 or ph or pw)
+        self.raw = torch.empty(2 * B, H, W, 3, dtype=torch.uint8 if u8 else torch.float32, device=d) if self.staged else None
+        self._shape = (B, H, W, u8)
         self._graph = None
 
     # ---- stages --------------------------------------------------------------------------------
@@ -81,8 +89,11 @@ class RaftEngine:
         kernels at 1/4 and 1/8 resolution: cnet runs on a forked stream beside fnet (a fork/join that is captured into
         the CUDA graph like the flow branch of the update block).  With defer_join the caller joins (`_join_cnet`)
         where cmap is first needed -- after the correlation volume, which only needs the feature maps."""
-        B = self._shape[0]
+        B, H, W, u8 = self._shape
         capi.check(capi.lib.rb_set_math_mode(self.math_mode))  # per-thread library state: set before ANY kernel of ours
+        if self.staged:  # F3: u8 -> fp32 /255 and replicate padding in one pass (csrc/frames.cu)
+            capi.check(capi.lib.rb_frames_prepare(capi.ptr(self.raw), int(u8), capi.ptr(self.images), 2 * B, H, W,
+                                                  *self.pad, capi.stream()))
         if self.torch_encoders:
             both = self.images * 2.0 - 1.0
             self.fmaps.copy_(self.fnet(both))  # instance norm is per sample, so batching left|right is exact
@@ -110,7 +121,7 @@ class RaftEngine:
 
     def _hot_path(self):
         """corr build + iterations + upsampling: hand-written kernels only (graph-capturable)."""
-        B, H, W = self._shape
+        B, H, W, _ = self._shape
         h, w, s, lib, st = self.h, self.w, int(self.small), capi.lib, capi.stream()
         capi.check(lib.rb_set_math_mode(self.math_mode))
         capi.check(lib.rb_corr_build(capi.ptr(self.fmap1), capi.ptr(self.fmap2), capi.ptr(self.pyramid), B, h, w,
@@ -120,11 +131,12 @@ class RaftEngine:
         capi.check(lib.rb_coords_grid(capi.ptr(self.coords1), B, h, w, st))
         capi.check(lib.rb_raft_iterate(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.pyramid),
                                        capi.ptr(self.coords1), capi.ptr(self.mask), B, h, w, self.iters, st))
+        top, left = self.pad[0], self.pad[2]  # crop the padding away while upsampling
         if self.small:
-            capi.check(lib.rb_upflow8(capi.ptr(self.coords1), capi.ptr(self.flow_up), B, h, w, 1.0, st))
+            capi.check(lib.rb_upflow8_crop(capi.ptr(self.coords1), capi.ptr(self.flow_up), B, h, w, 1.0, top, left, H, W, st))
         else:
-            capi.check(lib.rb_upsample_convex(capi.ptr(self.coords1), capi.ptr(self.mask), capi.ptr(self.flow_up),
-                                              B, h, w, st))
+            capi.check(lib.rb_upsample_convex_crop(capi.ptr(self.coords1), capi.ptr(self.mask), capi.ptr(self.flow_up),
+                                                   B, h, w, top, left, H, W, st))
 
     def _all(self):
         self.encode(defer_join=True)
@@ -160,16 +172,38 @@ class RaftEngine:
 
     @torch.no_grad()
     def forward(self, left: torch.Tensor, right: torch.Tensor) -> torch.Tensor:
-        """left/right: [B,H,W,3] fp32 CUDA tensors in [0,1] (BGR like the reference).  Returns the
-        [B,H,W,2] flow (a view of an engine-owned buffer, overwritten by the next call)."""
-        assert left.shape == right.shape and left.dim() == 4 and left.shape[-1] == 3
+        """left/right: [B,H,W,3] frames, BGR like the reference: fp32 in [0,1] (RAFT.inputs(), RAFT.py:45-51) or
+        uint8 in [0,255] (what cv2.imdecode yields, test_dataflow.py:56-61; the /255 then happens on the GPU).  Host
+        (ideally pinned) or CUDA tensors; any H, W >= 8.  Returns the [B,H,W,2] flow -- the engine-owned buffer itself,
+        overwritten by the next call (networks.RAFT.RAFT.forward hands out a copy)."""
+        assert left.shape == right.shape and left.dim() == 4 and left.shape[-1] == 3 and left.dtype == right.dtype
+        u8 = left.dtype == torch.uint8
+        assert u8 or left.dtype == torch.float32, left.dtype
         with torch.cuda.device(self.device):
             B = left.shape[0]
-            self._ensure(B, left.shape[1], left.shape[2])
-            self.images[:B].copy_(left, non_blocking=True)  # H2D when the caller hands pinned host tensors
-            self.images[B:].copy_(right, non_blocking=True)
+            self._ensure(B, left.shape[1], left.shape[2], u8)
+            dst = self.raw if self.staged else self.images
+            dst[:B].copy_(left, non_blocking=True)  # H2D when the caller hands pinned host tensors
+            dst[B:].copy_(right, non_blocking=True)
             self.run()
+            if not self._range_checked:
+                self._check_range()
         return self.flow_up
+
+    def _check_range(self):
+        """Once per engine: the split-operand format (fp16 hi/lo planes) saturates beyond 65504.  The fp32 tensors at
+        the boundary of that path are the feature maps, the context map and the correlation volume; a checkpoint that
+        drives them (or the result) out of range must fail loudly, not return a plausible-looking wrong flow."""
+        self._range_checked = True
+        if os.environ.get("RAFT_B200_NO_RANGE_CHECK"):
+            return
+        stats = torch.stack([self.fmaps.abs().max(), self.cmap.abs().max(),
+                             self.pyramid[:self.pyr_bytes // 4 - 64].abs().max(), self.flow_up.abs().max()]).tolist()
+        names = ("feature maps", "context map", "correlation volume", "flow")
+        for n, v in zip(names, stats):
+            if not np.isfinite(v) or (n != "flow" and v > 6.0e4):
+                raise capi.RaftB200Error(f"raft_b200: {n} reach |x|max = {v:.3g}: outside the fp16 range of the "
+                                         "split-operand tensor-core path (csrc/common.cuh)")
 
     def lowres_flow(self) -> torch.Tensor:
         g = torch.stack(torch.meshgrid(torch.arange(self.w, device=self.device),

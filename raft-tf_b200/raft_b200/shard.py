@@ -21,14 +21,24 @@ def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def sharded_forward(forward: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], left: torch.Tensor,
-                    right: torch.Tensor, gather: bool = True) -> torch.Tensor:
+                    right: torch.Tensor, gather: bool = True, device=None) -> torch.Tensor:
     """Run `forward` on this rank's slice of the batch; optionally all_gather the flows so that every rank
-    returns the full [B,H,W,2] result in the original order.  Works with any initialised process group."""
+    returns the full [B,H,W,2] result in the original order.  Works with any initialised process group.
+
+    `device`: where this rank's flows live (the engine's CUDA device).  Only needed for a rank whose shard is EMPTY
+    (B < world): its placeholder must sit on the same kind of device as the other ranks' results, not on the (possibly
+    host / pinned) input's device, or the NCCL all_gather would mix CPU and CUDA tensors."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     B = left.shape[0]
     lo, hi = shard_range(B, rank, world)
-    local = forward(left[lo:hi], right[lo:hi]) if hi > lo else left.new_zeros((0,) + tuple(left.shape[1:3]) + (2,))
+    if hi > lo:
+        local = forward(left[lo:hi], right[lo:hi])
+    else:
+        if device is None:
+            device = (torch.device("cuda", torch.cuda.current_device())
+                      if dist.is_initialized() and dist.get_backend() == "nccl" else left.device)
+        local = torch.zeros((0,) + tuple(left.shape[1:3]) + (2,), dtype=torch.float32, device=device)
     if world == 1 or not gather:
         return local
     sizes = [shard_range(B, r, world) for r in range(world)]

@@ -20,9 +20,26 @@ def load_npz(path: str) -> Dict[str, np.ndarray]:
         return out
 
 
+FP16_MAX = 65504.0
+
+
+def check_split_range(params: Dict[str, np.ndarray]) -> None:
+    """The tensor-core path carries every weight as an fp16 hi/lo pair (csrc/common.cuh): refuse checkpoints whose
+    conv weights do not fit instead of silently saturating them.  (He-initialised or trained RAFT weights are O(1).)"""
+    for k, v in params.items():
+        if k.endswith("/W") or k.endswith("/b"):
+            a = np.asarray(v)
+            if not np.isfinite(a).all():
+                raise ValueError(f"{k}: non-finite values in the checkpoint")
+            m = float(np.abs(a).max()) if a.size else 0.0
+            if m > FP16_MAX:
+                raise ValueError(f"{k}: |w|max = {m:.3g} exceeds the fp16 range of the split-operand format")
+
+
 def pack_update_block(params: Dict[str, np.ndarray], small: bool, device) -> torch.Tensor:
     """Pack ``update_block/*`` into the device blob rb_update_step consumes."""
     small_i = int(bool(small))
+    check_split_range({k: v for k, v in params.items() if k.startswith("update_block/")})
     n = capi.lib.rb_update_num_convs(small_i)
     Ws, bs, keep = (C.c_void_p * n)(), (C.c_void_p * n)(), []
     for i in range(n):

@@ -39,3 +39,18 @@ def test_cli_flags_match_reference():
                           ("--im1", "'frame_0010.png'"), ("--im2", "'frame_0011.png'"), ("--batch", "1")):
         assert flag in src and f"default={default}" in src, flag
     assert "'--small', action='store_true'" in src and "'-m', '--mode'" in src and "'-o', '--optimizer'" in src
+
+
+def test_flow_to_color_matches_reference_function_bit_for_bit():
+    """tests/golden/flow_to_color.npz = outputs of the reference's own flow_utils.flow_to_color (flow_utils.py:51-121)
+    run in-process by oracle/make_flowcolor_golden.py."""
+    fu = _load("flow_utils")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "flow_to_color.npz"))
+    assert np.array_equal(fu.make_colorwheel(), z["colorwheel"])
+    names = sorted({k.split("/")[0] for k in z.files if "/" in k})
+    assert len(names) >= 6
+    for n in names:
+        clip = float(z[n + "/clip"])
+        for bgr in (0, 1):
+            out = fu.flow_to_color(z[n + "/flow"], clip_flow=None if clip < 0 else clip, convert_to_bgr=bool(bgr))
+            assert np.array_equal(out, z[f"{n}/bgr{bgr}/out"]), (n, bgr)

@@ -1,0 +1,94 @@
+"""CUDA path vs the CPU oracle on the configurations BASELINE.json quotes the metric on, at FULL size and FULL
+iteration count (the oracle needs a few seconds per pair on the host cores):
+
+  configs[1]  raft-things  B=1  436x1024 (-> 440x1024)  32 iterations     (the headline: bench.py's workload)
+  configs[2]  raft-things  one sample of the B=8 540x960 (-> 544x960) batch, 32 iterations (grid 68x120: odd level dims)
+  configs[4]  raft-small   one sample of the 768x1024 batch, 20 iterations (grid 96x128)
+
+Tolerance: north_star's 1e-3 max-abs on the final flow field; the error and max|flow| are printed.  Batched runs
+equal per-sample runs bit for bit (test_gpu_fullsize.py), so one sample pins the whole batch."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import raft_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _pad(a, ph, pw):
+    return np.pad(a, ((0, 0), (ph // 2, ph - ph // 2), (pw // 2, pw - pw // 2), (0, 0)), mode="edge")
+
+
+def _case(cuda, small, H, W, iters, seed0=1000):
+    from raft_b200 import synth
+    from networks.RAFT import RAFT
+    p = synth.make_weights(small)
+    l, r = synth.make_batch(1, H, W, seed0=seed0)
+    ph, pw = (-H) % 8, (-W) % 8
+    ref = O.RAFTOracle(p, small=small, iters=iters).forward(torch.from_numpy(_pad(l, ph, pw)), torch.from_numpy(_pad(r, ph, pw)))
+    ref = ref[:, ph // 2:ph // 2 + H, pw // 2:pw // 2 + W]
+    m = RAFT((H, W, 3), SimpleNamespace(small=small), iters=iters, device=cuda).load(p)
+    out = m.forward(l, r).cpu()
+    assert out.shape == ref.shape == (1, H, W, 2)
+    err = (out - ref).abs().max().item()
+    print(f"\n{'small' if small else 'things'} {H}x{W} {iters} it: max-abs err {err:.3e}, max|flow| {ref.abs().max():.2f} px")
+    return err, m, l, r, out
+
+
+def test_config2_headline_436x1024_32_iterations(cuda):
+    err, m, l, r, out = _case(cuda, False, 436, 1024, 32)
+    assert err < TOL, err
+    # uint8 frames (cv2.imdecode's type; /255 on the GPU, csrc/frames.cu) give the same flow as the host-side
+    # np.float32(x)/255.0 of the reference (test_dataflow.py:96-97), bit for bit
+    l8, r8 = np.round(l * 255.0).astype(np.uint8), np.round(r * 255.0).astype(np.uint8)
+    a = m.forward(l8, r8)
+    b = m.forward(np.float32(l8) / np.float32(255.0), np.float32(r8) / np.float32(255.0))
+    assert torch.equal(a, b)
+    # results are fresh tensors (the reference returns a new array per session.run), not views of one buffer
+    assert a.data_ptr() != b.data_ptr()
+
+
+def test_config3_kitti_540x960_32_iterations(cuda):
+    err, *_ = _case(cuda, False, 540, 960, 32, seed0=1003)
+    assert err < TOL, err
+
+
+def test_config5_small_768x1024_20_iterations(cuda):
+    err, *_ = _case(cuda, True, 768, 1024, 20, seed0=1005)
+    assert err < TOL, err
+
+
+def test_sintel_pair_through_the_cli(cuda, tmp_path, monkeypatch):
+    """The reference's own sample pair (frame_0016/17.png, 436x1024) through infer_raft.py: cv2 decode, --keep-size
+    (replicate-pad to 440), 12 iterations, seeded weights saved in the reference's npz naming; compared with the oracle
+    on the identically decoded frames.  Also the reference default (bilinear resize to 432x1024)."""
+    import os
+    import cv2
+    from raft_b200 import synth
+    import infer_raft
+    data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    im1, im2 = os.path.join(data, "frame_0016.png"), os.path.join(data, "frame_0017.png")
+    p = synth.make_weights(False)
+    npz = str(tmp_path / "raft-things.npz")
+    np.savez(npz, **p)
+    monkeypatch.chdir(tmp_path)
+    for keep in (True, False):
+        npy = str(tmp_path / f"flow_{int(keep)}.npy")
+        argv = ["--im1", im1, "--im2", im2, "--load", npz, "--iters", "12", "--npy", npy] + (["--keep-size"] if keep else [])
+        assert infer_raft.main(argv) == 0
+        flow = np.load(npy)
+        l, r = infer_raft.read_pair(im1, im2, None if keep else (432, 1024))
+        H = l.shape[1]
+        ph = (-H) % 8
+        ref = O.RAFTOracle(p, iters=12).forward(torch.from_numpy(_pad(l, ph, 0)), torch.from_numpy(_pad(r, ph, 0)))
+        ref = ref[0, ph // 2:ph // 2 + H].numpy()
+        assert flow.shape == ref.shape == (H, 1024, 2)
+        err = np.abs(flow - ref).max()
+        print(f"\nsintel pair keep_size={keep}: max-abs err {err:.3e}, max|flow| {np.abs(ref).max():.2f} px")
+        assert err < TOL, err
+        png = cv2.imread(str(tmp_path / "raft_flow_raft-things.png"))
+        assert png is not None and png.shape == (H, 1024, 3)

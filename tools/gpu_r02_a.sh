@@ -1,0 +1,40 @@
+#!/bin/bash
+# Round 2, first GPU pass (one GPU): full parity suite, bench lines of both arms, lookup v4/v5 A/B, ncu evidence.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -q -m gpu --timeout 900 -x 2>&1 | tail -15 | tee $O/pytest_gpu.log
+echo "== bench (ours)"
+timeout 900 python bench.py 2>$O/bench_err.log | tail -1 | tee $O/bench_default.json | cut -c1-1500
+echo "== bench (reference arm, 2 steps)"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee $O/bench_reference.json | cut -c1-600
+echo "== lookup A/B"
+for B in 1 8; do
+  for fl in "" "--flush"; do
+    echo -n "v5 promo=none B=$B $fl: "; timeout 200 python tools/micro.py lookup --B $B $fl 2>&1 | tail -1
+    echo -n "v4            B=$B $fl: "; RAFT_B200_LOOKUP_V4=1 timeout 200 python tools/micro.py lookup --B $B $fl 2>&1 | tail -1
+  done
+  for pr in 64 128 256; do
+    echo -n "v5 promo=$pr B=$B --flush: "; RAFT_B200_LOOKUP_L2PROMO=$pr timeout 200 python tools/micro.py lookup --B $B --flush 2>&1 | tail -1
+  done
+done 2>&1 | tee $O/lookup_ab.log
+echo "== stage timings"
+for w in corr encoder update iterate; do timeout 200 python tools/micro.py $w 2>&1 | tail -1; done | tee $O/stages.log
+timeout 200 python tools/micro.py corr --flush 2>&1 | tail -1 | tee -a $O/stages.log
+echo "== ncu launch list (one forward, no graph)"
+RAFT_B200_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file $O/r02_launches.csv \
+    python tools/micro.py forward > $O/ncu_launches.log 2>&1
+echo "== ncu full: lookup v5 B=1 / B=8"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:corr_lookup -s 2 -c 1 -f -o $O/r02_lookup_b1 \
+    python tools/micro.py lookup --reps 3 --n 1 > $O/ncu_lookup1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:corr_lookup -s 2 -c 1 -f -o $O/r02_lookup_b8 \
+    python tools/micro.py lookup --B 8 --reps 3 --n 1 > $O/ncu_lookup8.log 2>&1
+echo "== ncu full: corr build (level-0 GEMM + the rest)"
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|split_rows|pool_fmap" -s 12 -c 12 -f -o $O/r02_corr \
+    python tools/micro.py corr --reps 1 --n 1 > $O/ncu_corr.log 2>&1
+echo "== ncu full: update-step convs"
+RAFT_B200_NO_PDL=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|flow_conv7" -s 15 -c 11 -f -o $O/r02_update \
+    python tools/micro.py update --reps 2 --n 1 > $O/ncu_update.log 2>&1
+ls -la $O | tail -12
