@@ -133,6 +133,21 @@ int rb_update_step(int small, const void* weights, void* workspace, float* coord
 int rb_raft_iterate(int small, const void* weights, void* workspace, const float* pyramid,
                     float* coords1, float* mask_out, int B, int h, int w, int iters, void* stream);
 
+/* ---- F2: volume-free correlation -- GetCorrPyramid + SampleCorr (model_utils.py:199-249) without the
+ * 4*N^2-byte volume.  Level l of the pyramid equals fmap1 . pool^l(fmap2)^T / sqrt(C) (pooling is linear), so each
+ * iteration evaluates only the (2r+3) x (2r+3) entries per pixel and level that the bilinear taps can touch, as fp32
+ * dot products against the pooled feature maps, and applies the same tap arithmetic as rb_corr_lookup.  Results equal
+ * the materialised path up to the summation order / operand rounding of the dot products (parity is on the flow, 1e-3).
+ * rb_corr_otf_prepare pools fmap2 once per pair into `workspace` (levels 1..3, fp32); C <= 256, multiple of 4. */
+int rb_corr_otf_workspace_bytes(int B, int h, int w, int C, size_t* bytes);
+int rb_corr_otf_prepare(const float* fmap2, void* workspace, size_t workspace_bytes, int B, int h, int w, int C,
+                        void* stream);
+int rb_corr_otf_lookup(const float* fmap1, const float* fmap2, const void* workspace, const float* coords,
+                       float* out, int B, int h, int w, int C, int radius, void* stream);
+/* lookup written straight into the update workspace (the volume-free counterpart of rb_update_lookup) */
+int rb_update_lookup_otf(int small, void* workspace, const float* fmap1, const float* fmap2,
+                         const void* otf_workspace, const float* coords1, int B, int h, int w, int C, void* stream);
+
 /* ---- A13: RAFT.upsample_flow (RAFT.py:119-134) and upflow8 (utils.py:105-111) ----------------
  * flow = coords1 - coords_grid is formed inside; out: [B,8h,8w,2]. */
 int rb_upsample_convex(const float* coords1, const float* mask, float* out, int B, int h, int w,

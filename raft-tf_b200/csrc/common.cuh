@@ -84,7 +84,10 @@ enum Epilogue : int {
   EPI_ZR = 1,     // c<hidden: z=sigmoid -> f0 ; else r=sigmoid, r*h(f1) -> d0
   EPI_Q = 2,      // q=tanh ; h=(1-z)h+zq -> f1 and d0
   EPI_DELTA = 3,  // c<2: coords1(f1)[c] += v ; optional copy to f2
-  EPI_F32 = 4     // f0[pix*cout+c] = scale*v
+  EPI_F32 = 4,    // f0[pix*cout+c] = scale*v
+  EPI_FH2 = 5     // flow_head/conv1 with conv2 folded in (tensor-core back end only): y = relu(acc+bias) is NOT stored; each
+                  // epilogue thread forms the 18 per-pixel dot products <y[c..], W2[tap][c..][o]> of ITS channels ->
+                  // fh2_part[pix][part][tap*2+o]; fh2_gather_kernel (update.cu) sums parts and 3x3 neighbours
 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1 };
 
@@ -103,6 +106,9 @@ struct ConvParams {
   const float* flow_tail;  // EPI_ACT, 16-channel epilogue: coords1; the last two channels are written as flow = coords1 - grid
   double* stat_part;  // EPI_F32 + tensor-core wide epilogue: per-(sample, strip, channel) sum / sum of squares of the
   int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
+  const float* fh2_w;  // EPI_FH2: fp32 [cout][20] = flow_head/conv2 weights W2[tap][c][o] at [c][tap*2+o] (18 used), per OUTPUT channel c of this conv
+  float* fh2_part;     // EPI_FH2: [pixel][fh2_parts][18] partial dot products; part = cout-tile * column groups + column group
+  int fh2_parts;
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue
   long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py

@@ -295,9 +295,10 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
 //   * every warp is self-contained (own mbarrier, own staging row, __syncwarp only): no block-wide barrier after the
 //     prologue; the fp16 hi/lo split happens in the output pass on 8 consecutive channels per lane (128-bit stores).
 // ---------------------------------------------------------------------------------------------
-template <int R>
+template <int R, bool OTF = false>
 struct LookupV5 {
-  static constexpr int D = 2 * R + 1, K = D * D, COLS = 12, ROWS = D + 1, PITCH = COLS * 4;
+  // OTF (volume-free): the patch is COMPUTED (dot products against pooled fmap2), with the slack row included
+  static constexpr int D = 2 * R + 1, K = D * D, COLS = 12, ROWS = OTF ? D + 2 : D + 1, PITCH = COLS * 4;
   static constexpr int SLOT = (ROWS * PITCH + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
   static constexpr int PB = 16, WARPS = PB, NT = WARPS * 32, ROUNDS = (K + 31) / 32;
   static constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel (324 -> 328, 196 -> 200)
@@ -305,7 +306,15 @@ struct LookupV5 {
   static constexpr int kTabOff = PB * 4 * SLOT;
   static constexpr int kStageOff = kTabOff + PB * 4 * TABN * 16;
   static constexpr int kBarOff = kStageOff + PB * OUTP * 4;
-  static constexpr int kBytes = kBarOff + WARPS * 8;
+  static constexpr int kF1Off = kBarOff + 128;  // OTF: fmap1 row of each warp's pixel, [PB][C <= 256] fp32
+  static constexpr int kBytes = kF1Off + (OTF ? PB * 256 * 4 : 0);
+};
+// volume-free mode: level l of the pyramid is fmap1 . pool^l(fmap2)^T / sqrt(C) (exact by linearity, gemm_tc.cu); here the
+// (2r+3) x 11 entries a unit can touch are evaluated on the fly instead of being read from a materialised volume.
+struct OtfView {
+  const float* f1;                 // [B,h,w,C]
+  const float* f2[RB_NUM_LEVELS];  // pooled fmap2, level l: [B, h>>l, w>>l, C] fp32
+  int C, N;                        // channels (<= 256, multiple of 4), pixels per sample (h*w)
 };
 struct PyramidMapsV5 {
   CUtensorMap m[RB_NUM_LEVELS];  // (W_l, H_l, B*N) fp32, box (12, 2r+2, 1), no swizzle, no L2 promotion
@@ -317,31 +326,35 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
-template <int R, bool SPLIT>
-__global__ void __launch_bounds__(LookupV5<R>::NT, 3)
+template <int R, bool SPLIT, bool OTF = false>
+__global__ void __launch_bounds__(LookupV5<R, OTF>::NT, 3)
 corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMapsV5 maps,
                       const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
-                      __half* __restrict__ out_lo, int out_stride, int npix) {
-  using L = LookupV5<R>;
+                      __half* __restrict__ out_lo, int out_stride, int npix, const OtfView otf) {
+  using L = LookupV5<R, OTF>;
   constexpr int D = L::D, K = L::K;
   extern __shared__ __align__(1024) uint8_t lk5_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pix = blockIdx.x * L::PB + warp;
   float4* tab = reinterpret_cast<float4*>(lk5_smem + L::kTabOff) + warp * 4 * L::TABN;
   float* stage = reinterpret_cast<float*>(lk5_smem + L::kStageOff) + warp * L::OUTP;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(lk5_smem + L::kBarOff) + warp;
+  // ONE mbarrier per block at a block-uniform address (the v4 pattern).  A per-warp barrier has a warp-dependent address:
+  // ptxas then emulates mbarrier.init with STS.64 + SYNCS.CCTL.IVALL instead of SYNCS.EXCH, and the first r02 build of this
+  // kernel (per-warp barriers) died with "illegal instruction" on the B200 -- not worth the ~1 us of decoupling.
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lk5_smem + L::kBarOff);
   uint8_t* patch = lk5_smem + warp * 4 * L::SLOT;
   const uint32_t patch_u32 = tc::smem_u32(patch);
   const bool live = pix < npix;
 
   int n_tma = 0;
 #pragma unroll
-  for (int l = 0; l < 4; ++l) n_tma += pv.tma_ok[l] ? 1 : 0;
-  if (lane == 0) {
+  for (int l = 0; l < 4; ++l) n_tma += (!OTF && pv.tma_ok[l]) ? 1 : 0;
+  if (threadIdx.x == 0) {
     tc::mbar_init(bar, 1);
     tc::fence_barrier_init();
     tc::fence_proxy_async();
-    if (n_tma && live) tc::mbar_arrive_expect_tx(bar, (uint32_t)(n_tma * L::ROWS * L::PITCH));
+    const int live_px = min(L::PB, npix - (int)blockIdx.x * L::PB);  // >= 1: the grid covers npix
+    if (n_tma) tc::mbar_arrive_expect_tx(bar, (uint32_t)(live_px * n_tma * L::ROWS * L::PITCH));
   }
   if (lane < L::OUTP - 4 * K) stage[4 * K + lane] = 0.f;  // channel padding of the staged row
   // taps of this lane: t = lane + 32*round = i*D + j   (i walks x, j walks y: model_utils.py:235-237)
@@ -352,7 +365,7 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     ti[rd] = t / D;
     tj[rd] = t - ti[rd] * D;
   }
-  __syncwarp();
+  __syncthreads();  // barrier initialised before any warp can issue a TMA that signals it (the only block-wide barrier)
   // PDL: dependents may be scheduled from here on (their own griddepcontrol.wait still waits for this grid to finish);
   // nothing above touched global memory, everything below comes after the predecessor kernel.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -368,7 +381,7 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     const int H = pv.hl[k], W = pv.wl[k];
     bx = min(max((int)__fadd_rn(c.x * inv, (float)(-R)), 0), W - 1);
     by = min(max((int)__fadd_rn(c.y * inv, (float)(-R)), 0), H - 1);
-    if (lane < 4 && pv.tma_ok[k]) tc::tma_load_3d(&maps.m[k], bar, patch + k * L::SLOT, bx, by, pix);
+    if (!OTF && lane < 4 && pv.tma_ok[k]) tc::tma_load_3d(&maps.m[k], bar, patch + k * L::SLOT, bx, by, pix);
   }
   // ---- index tables: lane -> (unit k = lane >> 3, entry e = lane & 7); entry 8 (r = 4) by the lanes with e = 0 / 1 ------
   unsigned bad = 0;
@@ -407,8 +420,34 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     }
   }
   const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);  // bits 8k..8k+7 belong to unit k
+  // ---- volume-free mode: evaluate the patch entries -- lane = entry (row, col), sequential fp32 dot product over C ------
+  if constexpr (OTF) {
+    float* f1s = reinterpret_cast<float*>(lk5_smem + L::kF1Off) + warp * 256;
+    const int C = otf.C;
+    for (int ch = lane * 4; ch < C; ch += 128)
+      *reinterpret_cast<float4*>(f1s + ch) = __ldg(reinterpret_cast<const float4*>(otf.f1 + (size_t)pix * C + ch));
+    __syncwarp();
+    const int b = pix / otf.N;
+    const float sq = sqrtf((float)C);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
+      const int H = pv.hl[k], W = pv.wl[k];
+      for (int e = lane; e < L::ROWS * 11; e += 32) {  // columns 0..10 (= D+1 + rounding slack at r = 4) can be indexed
+        const int row = e / 11, col = e - row * 11;
+        const float* f2 = otf.f2[k] + (((size_t)b * H + min(byk + row, H - 1)) * W + min(bxk + col, W - 1)) * C;
+        float acc = 0.f;
+        for (int ch = 0; ch < C; ch += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(f1s + ch);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(f2 + ch));
+          acc = fmaf(a.x, v.x, acc); acc = fmaf(a.y, v.y, acc); acc = fmaf(a.z, v.z, acc); acc = fmaf(a.w, v.w, acc);
+        }
+        *reinterpret_cast<float*>(patch + k * L::SLOT + row * L::PITCH + col * 4) = __fdiv_rn(acc, sq);  // divide AFTER the matmul (:213)
+      }
+    }
+  }
   // ---- levels TMA cannot address (W % 4 != 0): plain loads into the same layout ------------------------------------------
-  if (n_tma < 4) {
+  if (!OTF && n_tma < 4) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (pv.tma_ok[k]) continue;
@@ -426,14 +465,11 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     }
   }
   __syncwarp();  // tables and fallback patches visible to the warp
-  if (n_tma) {
-    if (lane == 0) tc::mbar_wait(bar, 0);  // one polling lane ...
-    __syncwarp();
-    tc::mbar_wait(bar, 0);                 // ... then every lane observes the completed phase (returns at once)
-  }
+  if (n_tma) tc::mbar_wait(bar, 0);  // all patches of the block have landed
   // ---- taps -----------------------------------------------------------------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);  // converged here (slow path only)
     const float4* xt = tab + k * L::TABN;
     const float4* yt = xt + D;
     const uint32_t pb = patch_u32 + k * L::SLOT;
@@ -447,11 +483,10 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
         const float wc = __fmul_rn(X.y, Y.x), wd = __fmul_rn(X.y, Y.y);
         const int a0 = __float_as_int(X.z), a1 = __float_as_int(X.w), r0 = __float_as_int(Y.z), r1 = __float_as_int(Y.w);
         float Ia, Ib, Ic, Id;
-        if (!slow) {
+        if (OTF || !slow) {
           Ia = lds_f32(pb + r0 + a0); Ib = lds_f32(pb + r1 + a0);
           Ic = lds_f32(pb + r0 + a1); Id = lds_f32(pb + r1 + a1);
         } else {  // rounding slack outside the box: read the four texels from the volume itself
-          const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
           const int H = pv.hl[k], W = pv.wl[k];
           const float* img = pv.base[k] + (size_t)pix * H * W;
           const int x0 = bxk + (a0 >> 2), x1 = bxk + (a1 >> 2), y0 = byk + r0 / L::PITCH, y1 = byk + r1 / L::PITCH;
@@ -557,15 +592,15 @@ static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, con
   return RB_OK;
 }
 
-template <int R, bool SPLIT>
+template <int R, bool SPLIT, bool OTF = false>
 static int launch_lookup_v5(const PyramidView& pv, const PyramidMapsV5& maps, const float2* c2, float* out_f32, __half* out_hi,
-                            __half* out_lo, int out_stride, int npix, cudaStream_t s) {
-  using L = LookupV5<R>;
+                            __half* out_lo, int out_stride, int npix, cudaStream_t s, const OtfView& otf = OtfView{}) {
+  using L = LookupV5<R, OTF>;
   static PerDeviceOnce attr_set;
   int dev = 0, rc_dev;
   if ((rc_dev = current_device(&dev))) return rc_dev;
   if (!attr_set.test(dev)) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_v5_kernel<R, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(corr_lookup_v5_kernel<R, SPLIT, OTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
     attr_set.set(dev);
   }
   static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
@@ -580,7 +615,7 @@ static int launch_lookup_v5(const PyramidView& pv, const PyramidMapsV5& maps, co
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_v5_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix));
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_v5_kernel<R, SPLIT, OTF>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix, otf));
   RB_CHECK_LAUNCH("corr_lookup_v5_kernel");
   return RB_OK;
 }
@@ -628,6 +663,50 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
                  : launch_lookup_cfg<4, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
   return split ? launch_lookup_cfg<3, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
                : launch_lookup_cfg<3, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
+}
+
+// ---- F2: volume-free correlation ---------------------------------------------------------------------------------------------
+// workspace = pooled fmap2 levels 1..3 (fp32); level 0 is the caller's fmap2 itself
+static size_t otf_level_offset(int B, int h, int w, int C, int level) {  // floats; level 1..4 (4 = total)
+  size_t off = 0;
+  for (int l = 1; l < level; ++l) off += (size_t)B * level_dim(h, l) * level_dim(w, l) * C;
+  return off;
+}
+__global__ void otf_pool_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int hs, int ws, int hd, int wd, int C) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // 2x2 VALID average pool of an NHWC map (model_utils.py:217-219 by linearity)
+  if (i >= (size_t)B * hd * wd * C) return;
+  int c = i % C;
+  size_t t = i / C;
+  int x = t % wd; t /= wd;
+  int y = t % hd;
+  int b = t / hd;
+  const float* p = src + (((size_t)b * hs + 2 * y) * ws + 2 * x) * C + c;
+  dst[i] = (p[0] + p[C] + p[(size_t)ws * C] + p[(size_t)ws * C + C]) * 0.25f;
+}
+int launch_lookup_otf(const float* fmap1, const float* fmap2, const float* pooled, const float* coords, float* out_f32,
+                      __half* out_hi, __half* out_lo, int out_stride, int B, int h, int w, int C, int radius, cudaStream_t s) {
+  RB_REQUIRE(radius == 3 || radius == 4, RB_ERR_UNSUPPORTED, "radius %d unsupported", radius);
+  RB_REQUIRE(C > 0 && C <= 256 && C % 4 == 0, RB_ERR_BAD_SHAPE, "volume-free lookup: C=%d (need a multiple of 4, <= 256)", C);
+  RB_REQUIRE((h >> 3) >= 1 && (w >> 3) >= 1, RB_ERR_BAD_SHAPE, "volume-free lookup: grid %dx%d too small for 4 levels", h, w);
+  RB_REQUIRE(out_hi == nullptr || out_stride % 8 == 0, RB_ERR_BAD_SHAPE, "lookup: split output stride %d", out_stride);
+  PyramidView pv;
+  memset(&pv, 0, sizeof(pv));
+  OtfView otf;
+  otf.f1 = fmap1; otf.C = C; otf.N = h * w;
+  for (int l = 0; l < RB_NUM_LEVELS; ++l) {
+    pv.hl[l] = level_dim(h, l); pv.wl[l] = level_dim(w, l);
+    otf.f2[l] = l == 0 ? fmap2 : pooled + otf_level_offset(B, h, w, C, l);
+  }
+  PyramidMapsV5 maps;
+  memset(&maps, 0, sizeof(maps));
+  const float2* c2 = reinterpret_cast<const float2*>(coords);
+  const int npix = B * h * w;
+  const bool split = out_hi != nullptr;
+  if (radius == 4)
+    return split ? launch_lookup_v5<4, true, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s, otf)
+                 : launch_lookup_v5<4, false, true>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s, otf);
+  return split ? launch_lookup_v5<3, true, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s, otf)
+               : launch_lookup_v5<3, false, true>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s, otf);
 }
 
 int corr_build_tc(const float* fmap1, const float* fmap2, float* pyramid, int B, int h, int w, int C,
@@ -714,4 +793,41 @@ extern "C" int rb_corr_lookup(const float* pyramid, const float* coords, float* 
   RB_REQUIRE(B > 0 && h > 0 && w > 0, RB_ERR_BAD_SHAPE, "rb_corr_lookup: bad shape");
   int K = (2 * radius + 1) * (2 * radius + 1);
   return launch_lookup(pyramid, coords, out, nullptr, nullptr, 4 * K, B, h, w, radius, (cudaStream_t)stream);
+}
+
+/* ---- F2: volume-free correlation; same results as rb_corr_build + rb_corr_lookup up to fp32 summation order ---- */
+extern "C" int rb_corr_otf_workspace_bytes(int B, int h, int w, int C, size_t* bytes) {
+  RB_REQUIRE(bytes && B > 0 && h > 0 && w > 0 && C > 0, RB_ERR_BAD_ARG, "rb_corr_otf_workspace_bytes: bad argument");
+  *bytes = otf_level_offset(B, h, w, C, RB_NUM_LEVELS) * sizeof(float) + 256;
+  return RB_OK;
+}
+
+extern "C" int rb_corr_otf_prepare(const float* fmap2, void* workspace, size_t workspace_bytes, int B, int h, int w, int C,
+                                   void* stream) {
+  RB_REQUIRE(fmap2 && workspace, RB_ERR_BAD_ARG, "rb_corr_otf_prepare: null pointer");
+  RB_REQUIRE(B > 0 && (h >> 3) >= 1 && (w >> 3) >= 1 && C > 0, RB_ERR_BAD_SHAPE, "rb_corr_otf_prepare: bad shape");
+  size_t need;
+  rb_corr_otf_workspace_bytes(B, h, w, C, &need);
+  RB_REQUIRE(workspace_bytes >= need, RB_ERR_WORKSPACE, "rb_corr_otf_prepare: workspace has %zu bytes, need %zu", workspace_bytes, need);
+  float* pooled = reinterpret_cast<float*>(workspace);
+  const float* prev = fmap2;
+  for (int l = 1; l < RB_NUM_LEVELS; ++l) {
+    float* dst = pooled + otf_level_offset(B, h, w, C, l);
+    const int hd = level_dim(h, l), wd = level_dim(w, l);
+    const size_t n = (size_t)B * hd * wd * C;
+    otf_pool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prev, dst, B, level_dim(h, l - 1), level_dim(w, l - 1),
+                                                                                 hd, wd, C);
+    RB_CHECK_LAUNCH("otf_pool_kernel");
+    prev = dst;
+  }
+  return RB_OK;
+}
+
+extern "C" int rb_corr_otf_lookup(const float* fmap1, const float* fmap2, const void* workspace, const float* coords, float* out,
+                                  int B, int h, int w, int C, int radius, void* stream) {
+  RB_REQUIRE(fmap1 && fmap2 && workspace && coords && out, RB_ERR_BAD_ARG, "rb_corr_otf_lookup: null pointer");
+  RB_REQUIRE(B > 0 && h > 0 && w > 0, RB_ERR_BAD_SHAPE, "rb_corr_otf_lookup: bad shape");
+  const int K = (2 * radius + 1) * (2 * radius + 1);
+  return launch_lookup_otf(fmap1, fmap2, reinterpret_cast<const float*>(workspace), coords, out, nullptr, nullptr, 4 * K, B, h, w, C,
+                           radius, (cudaStream_t)stream);
 }

@@ -23,6 +23,8 @@ namespace rb {
 
 int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
                   __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s);
+int launch_lookup_otf(const float* fmap1, const float* fmap2, const float* pooled, const float* coords, float* out_f32,
+                      __half* out_hi, __half* out_lo, int out_stride, int B, int h, int w, int C, int radius, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // static description of the two variants
@@ -82,6 +84,7 @@ struct PackedLayout {
   size_t hi[P_COUNT], lo[P_COUNT], bias[P_COUNT];  // byte offsets
   int cout[P_COUNT], cout_pad[P_COUNT], kh[P_COUNT], kw[P_COUNT];
   size_t f1_w, f1_b;  // convf1: fp32 [49*2][cout] and bias
+  size_t fh2_w;       // flow_head/conv2 as fp32 [fh][20]: W2[tap][c][o] at [c][tap*2+o] (18 used) -- EPI_FH2 epilogue of conv1
   size_t total;
 };
 
@@ -106,6 +109,7 @@ static PackedLayout packed_layout(const Variant& v) {
   const RefConv& f = v.ref[v.convf1_ref];
   L.f1_w = off; off = align_up(off + (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float), 256);
   L.f1_b = off; off = align_up(off + (size_t)f.cout * sizeof(float), 256);
+  L.fh2_w = off; off = align_up(off + (size_t)v.fh * 20 * sizeof(float), 256);
   L.total = off;
   return L;
 }
@@ -117,8 +121,10 @@ struct Workspace {
   float* Z;
   float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
   unsigned int* counters;  // grid-barrier counters of the fused update-step kernel (update_fused.cu)
+  float* fh2_part;         // [npix][kFh2MaxParts][18]: per-pixel partial products of the folded flow_head/conv2 (EPI_FH2)
   size_t total;
 };
+constexpr int kFh2MaxParts = 16;
 
 static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
   Workspace W;
@@ -151,6 +157,8 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
   }
   W.counters = reinterpret_cast<unsigned int*>(b + off);
   off += 1024;
+  W.fh2_part = reinterpret_cast<float*>(b + off);
+  off += align_up(npix * (size_t)kFh2MaxParts * 18 * sizeof(float), 1024);
   W.total = off;
   return W;
 }
@@ -447,6 +455,57 @@ static int launch_flow_head2(const ConvParams& p, cudaStream_t s) {
   return RB_OK;
 }
 
+// flow_head/conv2 folded into conv1 (EPI_FH2): conv1's epilogue left, per pixel q and part s (cout tile x column group),
+// G[q][s][tap*2+o] = sum over the part's channels of relu(conv1)[q][c] * W2[tap][c][o].  The 3x3 conv (SAME: zero outside
+// the image) is then  delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o]  -- fixed summation order
+// (tap-major, parts ascending): bit-reproducible, batched == per-sample.  coords1 += delta (RAFT.py:102).
+__global__ void __launch_bounds__(64) fh2_gather_kernel(const float* __restrict__ part, int parts, const float* __restrict__ bias,
+                                                        float* coords1, float* delta_out, int B, int h, int w) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * h * w) return;
+  const int x = i % w, y = (i / w) % h, b = i / (w * h);
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+    const float* g = part + ((size_t)((b * h + yy) * w + xx) * parts) * 18 + t * 2;
+    for (int s = 0; s < parts; ++s) {
+      const float2 v = *reinterpret_cast<const float2*>(g + s * 18);
+      d0 += v.x;
+      d1 += v.y;
+    }
+  }
+  d0 += bias[0];
+  d1 += bias[1];
+  float2 c = *reinterpret_cast<float2*>(coords1 + (size_t)i * 2);
+  c.x += d0; c.y += d1;
+  *reinterpret_cast<float2*>(coords1 + (size_t)i * 2) = c;
+  if (delta_out) *reinterpret_cast<float2*>(delta_out + (size_t)i * 2) = make_float2(d0, d1);
+}
+
+static int launch_fh2_gather(const float* part, int parts, const float* bias, float* coords1, float* delta_out, int B, int h,
+                             int w, cudaStream_t s) {
+  static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((B * h * w + 63) / 64);
+  cfg.blockDim = dim3(64);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl;
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fh2_gather_kernel, part, parts, bias, coords1, delta_out, B, h, w));
+  RB_CHECK_LAUNCH("fh2_gather_kernel");
+  return RB_OK;
+}
+
+int conv_tc_fh2_parts(const ConvParams& p);
+
 // Phase-timestamp debug buffer (tools/phase_times.py): rb_debug_set_buffer(ptr, convs) makes the next update
 // step record 8 timestamps per CTA for each of its convs, in launch order, 4096 CTAs per conv.
 static thread_local long long* g_dbg = nullptr;
@@ -639,18 +698,35 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   {
     ConvParams p = base_params(v, L, blob, P_FH1, W.hx, v.hx, 0, B, h, w);
     set_act(p, ACT_RELU, W.fh, v.fh, 0);
+    // Default (tensor-core back end): conv2 (3x3, fh -> 2: as an implicit GEMM it used 2 of 16 MMA columns for ~15 us per
+    // iteration at batch 1) is folded into conv1's epilogue + a tiny gather kernel; conv1's activations are never stored.
+    // RAFT_B200_NO_FH2_FUSE=1: the two separate convs (A/B knob; also what the CUDA-core back end runs).
+    static const bool no_fuse = getenv("RAFT_B200_NO_FH2_FUSE") != nullptr;
+    bool fuse = !fused && !no_fuse && !g_dbg && math_mode() == RB_MATH_TC && p.cout % 16 == 0 && L.kh[P_FH2] == 3 && L.kw[P_FH2] == 3;
+    if (fuse) {
+      p.epi = EPI_FH2;
+      p.fh2_w = reinterpret_cast<const float*>(bb + L.fh2_w);
+      p.fh2_part = W.fh2_part;
+      p.fh2_parts = conv_tc_fh2_parts(p);
+      fuse = p.fh2_parts <= kFh2MaxParts;
+      if (!fuse) set_act(p, ACT_RELU, W.fh, v.fh, 0);
+    }
     if ((rc = launch_conv_dbg(p, s))) return rc;
-    p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
-    p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
-    // RAFT_B200_FH2_SIMT=1: CUDA-core kernel instead of the N=16 implicit GEMM.  Measured (profiles/r01_notes.md): 6 us
-    // per iteration faster without programmatic dependent launch, 7 us slower with it (the default) -> opt-in.
-    static const bool fh2_simt = getenv("RAFT_B200_FH2_SIMT") != nullptr;
-    const bool direct = !fused && fh2_simt && p.kh == 3 && p.kw == 3 && p.in_choff == 0 && p.in_stride % 8 == 0 &&
-                        (p.cin_pad == 256 || p.cin_pad == 128) && p.cout == 2;
-    if (direct) {
-      if ((rc = launch_flow_head2(p, s))) return rc;
-    } else if ((rc = launch_conv_dbg(p, s))) {
-      return rc;
+    if (fuse) {
+      const float* b2 = reinterpret_cast<const float*>(bb + L.bias[P_FH2]);
+      if ((rc = launch_fh2_gather(W.fh2_part, p.fh2_parts, b2, coords1, delta_out, B, h, w, s))) return rc;
+    } else {
+      p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
+      p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
+      // RAFT_B200_FH2_SIMT=1: CUDA-core kernel instead of the N=16 implicit GEMM (profiles/r01_notes.md) -> opt-in.
+      static const bool fh2_simt = getenv("RAFT_B200_FH2_SIMT") != nullptr;
+      const bool direct = !fused && fh2_simt && p.kh == 3 && p.kw == 3 && p.in_choff == 0 && p.in_stride % 8 == 0 &&
+                          (p.cin_pad == 256 || p.cin_pad == 128) && p.cout == 2;
+      if (direct) {
+        if ((rc = launch_flow_head2(p, s))) return rc;
+      } else if ((rc = launch_conv_dbg(p, s))) {
+        return rc;
+      }
     }
   }
   // ---- mask head (model_utils.py:180-183); only the last iteration's mask is ever consumed ----
@@ -768,6 +844,18 @@ extern "C" int rb_update_weights_pack(int small, const float* const* W_host, con
     memcpy(host.data() + L.f1_w, W_host[v.convf1_ref], (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float));
     memcpy(host.data() + L.f1_b, b_host[v.convf1_ref], (size_t)f.cout * sizeof(float));
   }
+  {  // flow_head/conv2 [3,3,fh,2] HWIO -> fp32 [fh][20], entry [c][tap*2+o]
+    int fh2_ref = -1;
+    for (int i = 0; i < v.nref; ++i)
+      if (strstr(v.ref[i].name, "flow_head/conv2")) fh2_ref = i;
+    RB_REQUIRE(fh2_ref >= 0 && v.ref[fh2_ref].cin == v.fh && v.ref[fh2_ref].cout == 2 && v.ref[fh2_ref].kh == 3, RB_ERR_BAD_SHAPE,
+               "internal: flow_head/conv2 shape");
+    float* dst = reinterpret_cast<float*>(host.data() + L.fh2_w);
+    const float* W2 = W_host[fh2_ref];
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < v.fh; ++c)
+        for (int o = 0; o < 2; ++o) dst[(size_t)c * 20 + t * 2 + o] = W2[((size_t)t * v.fh + c) * 2 + o];
+  }
   cudaStream_t s = (cudaStream_t)stream;
   RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), L.total, cudaMemcpyHostToDevice, s));
   RB_CHECK_CUDA(cudaStreamSynchronize(s));  // `host` dies at return; packing is an init-time call
@@ -833,6 +921,18 @@ extern "C" int rb_update_lookup(int small, void* workspace, const float* pyramid
   Workspace W = workspace_layout(v, (size_t)B * h * w, workspace);
   return launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius,
                        (cudaStream_t)stream);
+}
+
+/* volume-free form of rb_update_lookup (F2): correlation features straight from the feature maps */
+extern "C" int rb_update_lookup_otf(int small, void* workspace, const float* fmap1, const float* fmap2, const void* otf_workspace,
+                                    const float* coords1, int B, int h, int w, int C, void* stream) {
+  RB_REQUIRE(workspace && fmap1 && fmap2 && otf_workspace && coords1, RB_ERR_BAD_ARG, "rb_update_lookup_otf: null pointer");
+  int rc = check_shape("rb_update_lookup_otf", B, h, w);
+  if (rc) return rc;
+  const Variant& v = variant(small);
+  Workspace W = workspace_layout(v, (size_t)B * h * w, workspace);
+  return launch_lookup_otf(fmap1, fmap2, reinterpret_cast<const float*>(otf_workspace), coords1, nullptr, W.corr.hi, W.corr.lo,
+                           v.corr_pad, B, h, w, C, v.radius, (cudaStream_t)stream);
 }
 
 extern "C" int rb_update_set_corr(int small, void* workspace, const float* corr, int B, int h, int w,

@@ -21,7 +21,7 @@ class RAFT(object):
     weight_decay = 1e-5          # vestigial in the reference too (RAFT.py:14)
     data_format = 'NHWC'
 
-    def __init__(self, image_shape, args, iters=20, batch=1, device=None):
+    def __init__(self, image_shape, args, iters=20, batch=1, device=None, volume_free=None):
         self.dropout = 0.0
         self.corr_radius = 4
         self.hidden_dim = 128
@@ -36,6 +36,7 @@ class RAFT(object):
             self.context_dim = 64
             self.corr_radius = 3
         self.device = torch.device(device if device is not None else 'cuda:0')
+        self.volume_free = volume_free  # extension: None = RAFT_B200_VOLUME_FREE env, default off
         self.flow_result = None
         self._engine = None
         self._params = None
@@ -78,7 +79,8 @@ class RAFT(object):
         if self._engine is None:
             if self._params is None:
                 raise RuntimeError("RAFT.load(<npz>) must be called before inference")
-            self._engine = RaftEngine(self._params, small=self.small, iters=self.iters, device=self.device)
+            self._engine = RaftEngine(self._params, small=self.small, iters=self.iters, device=self.device,
+                                      volume_free=self.volume_free)
         return self._engine
 
     # -- inference ---------------------------------------------------------------------------------

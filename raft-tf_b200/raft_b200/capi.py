@@ -49,6 +49,10 @@ SIGNATURES = {
     "rb_update_set_corr": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_step": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_raft_iterate": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rb_corr_otf_workspace_bytes": (_i, [_i, _i, _i, _i, _psz]),
+    "rb_corr_otf_prepare": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "rb_corr_otf_lookup": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rb_update_lookup_otf": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rb_upsample_convex": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_upflow8": (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
     "rb_upsample_convex_crop": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -20,13 +20,18 @@ from .weights import pack_update_block
 
 class RaftEngine:
     def __init__(self, params: Dict[str, np.ndarray], small: bool = False, iters: int = 20,
-                 device: Optional[torch.device] = None, use_graph: bool = True, math_mode: int = capi.RB_MATH_TC):
+                 device: Optional[torch.device] = None, use_graph: bool = True, math_mode: int = capi.RB_MATH_TC,
+                 volume_free: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("raft_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda:0")
         self.small, self.iters = bool(small), int(iters)
         self.hidden, self.ctx, self.radius, self.fdim = (96, 64, 3, 128) if small else (128, 128, 4, 256)
         self.use_graph = use_graph and not os.environ.get("RAFT_B200_NO_GRAPH")
+        # F2 (opt-in): no materialised correlation volume -- every iteration evaluates the dot products its taps touch
+        # straight from the feature maps (rb_update_lookup_otf).  Saves 4*N^2*1.33 bytes per pair (261 MB at 440x1024),
+        # costs ~100 k extra FMA per pixel and iteration on the CUDA cores; same flow up to fp32 summation order.
+        self.volume_free = bool(os.environ.get("RAFT_B200_VOLUME_FREE")) if volume_free is None else bool(volume_free)
         self.math_mode = math_mode
         torch.backends.cudnn.allow_tf32 = False  # the reference is fp32 end to end (only matters for the cuDNN cross-check)
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -61,9 +66,13 @@ class RaftEngine:
         d = self.device
         lib = capi.lib
         self.h, self.w, self.Hp, self.Wp = h, w, Hp, Wp
-        self.pyr_bytes = capi.size_query(lib.rb_corr_pyramid_bytes, B, h, w)
-        self.pyramid = torch.empty(self.pyr_bytes // 4, dtype=torch.float32, device=d)
-        self.cws_bytes = capi.size_query(lib.rb_corr_workspace_bytes, B, h, w, self.fdim)
+        if self.volume_free:
+            self.pyr_bytes, self.pyramid = 0, None
+            self.cws_bytes = capi.size_query(lib.rb_corr_otf_workspace_bytes, B, h, w, self.fdim)  # pooled fmap2, levels 1..3
+        else:
+            self.pyr_bytes = capi.size_query(lib.rb_corr_pyramid_bytes, B, h, w)
+            self.pyramid = torch.empty(self.pyr_bytes // 4, dtype=torch.float32, device=d)
+            self.cws_bytes = capi.size_query(lib.rb_corr_workspace_bytes, B, h, w, self.fdim)
         self.corr_ws = torch.zeros(self.cws_bytes, dtype=torch.uint8, device=d)
         self.ws_bytes = capi.size_query(lib.rb_update_workspace_bytes, s, B, h, w)
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=d)  # zero fill = channel padding
@@ -124,13 +133,24 @@ class RaftEngine:
         B, H, W, _ = self._shape
         h, w, s, lib, st = self.h, self.w, int(self.small), capi.lib, capi.stream()
         capi.check(lib.rb_set_math_mode(self.math_mode))
-        capi.check(lib.rb_corr_build(capi.ptr(self.fmap1), capi.ptr(self.fmap2), capi.ptr(self.pyramid), B, h, w,
-                                     self.fdim, capi.ptr(self.corr_ws), self.cws_bytes, st))
+        if self.volume_free:
+            capi.check(lib.rb_corr_otf_prepare(capi.ptr(self.fmap2), capi.ptr(self.corr_ws), self.cws_bytes, B, h, w, self.fdim, st))
+        else:
+            capi.check(lib.rb_corr_build(capi.ptr(self.fmap1), capi.ptr(self.fmap2), capi.ptr(self.pyramid), B, h, w,
+                                         self.fdim, capi.ptr(self.corr_ws), self.cws_bytes, st))
         self._join_cnet()  # cmap (context encoder, forked stream) is first needed here
         capi.check(lib.rb_update_set_state_cnet(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.cmap), B, h, w, st))
         capi.check(lib.rb_coords_grid(capi.ptr(self.coords1), B, h, w, st))
-        capi.check(lib.rb_raft_iterate(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.pyramid),
-                                       capi.ptr(self.coords1), capi.ptr(self.mask), B, h, w, self.iters, st))
+        if self.volume_free:  # RAFT.py:91-102 with the lookup evaluated on the fly
+            for it in range(self.iters):
+                capi.check(lib.rb_update_lookup_otf(s, capi.ptr(self.ws), capi.ptr(self.fmap1), capi.ptr(self.fmap2),
+                                                    capi.ptr(self.corr_ws), capi.ptr(self.coords1), B, h, w, self.fdim, st))
+                mask = self.mask if (it == self.iters - 1 and not self.small) else None
+                capi.check(lib.rb_update_step(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.coords1), None,
+                                              capi.ptr(mask), B, h, w, st))
+        else:
+            capi.check(lib.rb_raft_iterate(s, capi.ptr(self.blob), capi.ptr(self.ws), capi.ptr(self.pyramid),
+                                           capi.ptr(self.coords1), capi.ptr(self.mask), B, h, w, self.iters, st))
         top, left = self.pad[0], self.pad[2]  # crop the padding away while upsampling
         if self.small:
             capi.check(lib.rb_upflow8_crop(capi.ptr(self.coords1), capi.ptr(self.flow_up), B, h, w, 1.0, top, left, H, W, st))
@@ -197,8 +217,8 @@ class RaftEngine:
         self._range_checked = True
         if os.environ.get("RAFT_B200_NO_RANGE_CHECK"):
             return
-        stats = torch.stack([self.fmaps.abs().max(), self.cmap.abs().max(),
-                             self.pyramid[:self.pyr_bytes // 4 - 64].abs().max(), self.flow_up.abs().max()]).tolist()
+        vol = self.pyramid[:self.pyr_bytes // 4 - 64].abs().max() if self.pyramid is not None else self.fmaps.new_zeros(())
+        stats = torch.stack([self.fmaps.abs().max(), self.cmap.abs().max(), vol, self.flow_up.abs().max()]).tolist()
         names = ("feature maps", "context map", "correlation volume", "flow")
         for n, v in zip(names, stats):
             if not np.isfinite(v) or (n != "flow" and v > 6.0e4):

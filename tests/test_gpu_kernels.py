@@ -55,6 +55,56 @@ def test_lookup_bit_exact(cuda, B, h, w, r):
     assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} taps differ; max abs diff {(out - ref).abs().max():.3e}"
 
 
+def test_lookup_rounding_slack_outside_the_box(cuda):
+    """fl(c + d) can round UP across an integer (c = 15.999999, d = +4 -> 20.0 while trunc(c - 4) + 8 = 19): the window then
+    reaches one row / column beyond the (2r+2)^2 footprint.  Lookup v5 stages (2r+2) rows and takes a per-tap global-load
+    path for such units; columns have the slack inside the 12-column box.  Must stay bit-exact."""
+    from networks.model_utils import SampleCorr
+    B, h, w, r = 1, 48, 64, 4
+    pyr = _rand_pyramid(B, h, w, 77)
+    coords = _coords(B, h, w, 3)
+    below = lambda v: float(np.nextafter(np.float32(v), np.float32(0)))  # noqa: E731  largest fp32 < v
+    k = 0
+    for cy in (16.0, 32.0, 8.0):
+        for cx in (16.0, 32.0, 10.5):
+            coords[0, 5 + k // 8, 8 + k % 8] = torch.tensor([below(cx) if cx != 10.5 else cx, below(cy)])
+            coords[0, 20 + k // 8, 8 + k % 8] = torch.tensor([below(cy), below(cx) if cx != 10.5 else 3.25])
+            k += 1
+    # the anomaly is really present: trunc(fl(c + 4)) - trunc(c - 4) == 9 for these coordinates
+    c = torch.tensor(below(16.0))
+    assert int(torch.trunc(c + 4.0)) - int(torch.trunc(c - 4.0)) == 9
+    ref = O.sample_corr(pyr, coords, radius=r)
+    out = SampleCorr([p.to(cuda) for p in pyr], coords.to(cuda), radius=r).cpu()
+    assert torch.equal(out, ref), f"{int((out != ref).sum())} taps differ"
+
+
+@pytest.mark.parametrize("B,h,w,C,r", [(1, 16, 32, 256, 4), (2, 17, 30, 128, 3), (1, 55, 128, 256, 4)])
+def test_volume_free_lookup_matches_materialised_path(cuda, B, h, w, C, r):
+    """F2: rb_corr_otf_lookup == SampleCorr(GetCorrPyramid(f1, f2)) up to the summation order / operand
+    rounding of the dot products, and both agree with the fp64 oracle (model_utils.py:199-249)."""
+    from raft_b200 import capi
+    from networks.model_utils import GetCorrPyramid, SampleCorr
+    g = torch.Generator().manual_seed(21)
+    f1 = torch.randn(B, h, w, C, generator=g)
+    f2 = torch.randn(B, h, w, C, generator=g)
+    coords = _coords(B, h, w, 17)
+    ref = O.sample_corr(O.get_corr_pyramid(f1.double(), f2.double()), coords.double(), radius=r)
+    f1d, f2d, cd = f1.to(cuda), f2.to(cuda), coords.to(cuda)
+    mat = SampleCorr(GetCorrPyramid(f1d, f2d), cd, radius=r).cpu()
+    lib = capi.lib
+    wsb = capi.size_query(lib.rb_corr_otf_workspace_bytes, B, h, w, C)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=cuda)
+    out = torch.empty(B, h, w, 4 * (2 * r + 1) ** 2, device=cuda)
+    capi.check(lib.rb_corr_otf_prepare(capi.ptr(f2d), capi.ptr(ws), wsb, B, h, w, C, capi.stream()))
+    capi.check(lib.rb_corr_otf_lookup(capi.ptr(f1d), capi.ptr(f2d), capi.ptr(ws), capi.ptr(cd), capi.ptr(out), B, h, w, C, r,
+                                      capi.stream()))
+    out = out.cpu()
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() < 2e-5 * scale
+    assert (mat.double() - ref).abs().max().item() < 2e-5 * scale
+    assert (out - mat).abs().max().item() < 2e-5 * scale
+
+
 def test_lookup_split_output_matches_fp32(cuda):
     """The fast path writes hi/lo fp16 planes; they must reconstruct the fp32 lookup to 2^-21 relative."""
     from raft_b200 import capi

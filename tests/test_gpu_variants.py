@@ -25,9 +25,17 @@ def _kernel_parity(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 
-@pytest.mark.parametrize("knob", ["RAFT_B200_NO_HOIST", "RAFT_B200_FH2_SIMT", "RAFT_B200_NO_PDL"])
+@pytest.mark.parametrize("knob", ["RAFT_B200_NO_HOIST", "RAFT_B200_NO_FH2_FUSE", "RAFT_B200_NO_PDL"])
 def test_variant_passes_conv_and_update_parity(cuda, knob):
     _kernel_parity(dict(os.environ, **{knob: "1"}))
+
+
+def test_round1_lookup_kernel_still_bit_exact(cuda):
+    """RAFT_B200_LOOKUP_V4=1 selects the round-1 lookup kernel (16-column swizzled boxes), kept as the A/B partner of v5."""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_kernels.py"), "-q", "-x",
+                        "-k", "lookup", "--timeout", "300", "-p", "no:cacheprovider"],
+                       env=dict(os.environ, RAFT_B200_LOOKUP_V4="1"), cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 
 @experiments
