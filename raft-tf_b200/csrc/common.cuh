@@ -109,6 +109,7 @@ struct ConvParams {
   const float* fh2_w;  // EPI_FH2: fp32 [cout][20] = flow_head/conv2 weights W2[tap][c][o] at [c][tap*2+o] (18 used), per OUTPUT channel c of this conv
   float* fh2_part;     // EPI_FH2: [pixel][fh2_parts][18] partial dot products; part = cout-tile * column groups + column group
   int fh2_parts;
+  int stash;      // 1: single-tile CTAs park the gate epilogues' fp32 operands in spare TMEM columns during the MMA loop
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue
   long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py
@@ -368,9 +369,40 @@ __device__ __forceinline__ void store16(const ConvParams& p, float* dst, const f
     dst[0] = 1.f;
   }
 }
+// ---- TMEM as a prefetch buffer for epilogue operands ("stash") -------------------------------------------------------
+// At batch 1 a conv CTA owns ONE tile, so the second accumulator buffer in TMEM is never used by the MMA warp.  The 16
+// epilogue warps idle during the MMA loop; they load the fp32 operands the gate epilogues need (hoisted addend, z, h) and
+// park them there with tcgen05.st -- after the loop the epilogue reads them back next to the accumulators (tcgen05.ld,
+// tens of cycles) instead of paying two dependent L2 round trips per 16-channel chunk with only 4 warps per scheduler
+// to hide them (r01 what-if: the epilogue's global loads cost 13 us per update step).  Holding them in registers instead
+// was tried in round 1 and spilled (96-register cap).  Layout: operand k of tile column c at TMEM column stash + k*BN + c.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// load + wait in one asm block: the registers are valid when it returns
+__device__ __forceinline__ void tmem_ld16_sync(uint32_t taddr, float* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+struct Stash {
+  uint32_t taddr;  // TMEM address (lane quarter of this warp, first stash column) or 0 = operands come from global memory
+  int bn;          // tile width = column distance between stashed operands
+  int cl;          // column of the current 16-channel chunk inside the tile
+};
+
 // WI: compile the RAFT_B200_WHATIF hooks in (fused kernel only; everything the default path runs stays lean)
 template <bool WI = false>
-__device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, int c, float* y) {
+__device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, int c, float* y, const Stash st = Stash{0, 0, 0}) {
   if (p.bias) {
     float t[16];
     ld256_nc(p.bias + c, t);
@@ -381,7 +413,9 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
   if (p.addend) {
     float t[16];
     const float* ad = p.addend + (size_t)pix * p.cout + c;
-    if (!WI || !(p.whatif & 128)) {
+    if (!WI && st.taddr) {
+      tmem_ld16_sync(st.taddr + st.cl, t);
+    } else if (!WI || !(p.whatif & 128)) {
       ld256_nc(ad, t);
       ld256_nc(ad + 8, t + 8);
     } else {
@@ -416,7 +450,8 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
       } else {
         const int ch = c - p.hidden;
         float hprev[16];
-        load16<WI>(p, p.f1 + (size_t)pix * p.hidden + ch, hprev);
+        if (!WI && st.taddr) tmem_ld16_sync(st.taddr + st.bn + st.cl, hprev);
+        else load16<WI>(p, p.f1 + (size_t)pix * p.hidden + ch, hprev);
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = sigmoid_f(y[i]) * hprev[i];
         store_split16<WI>(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + ch, y);
@@ -425,8 +460,13 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
     case EPI_Q: {
       float z[16], hprev[16];
       float* hp = p.f1 + (size_t)pix * p.hidden + c;
-      load16<WI>(p, p.f0 + (size_t)pix * p.hidden + c, z);
-      load16<WI>(p, hp, hprev);
+      if (!WI && st.taddr) {
+        tmem_ld16_sync(st.taddr + st.bn + st.cl, z);
+        tmem_ld16_sync(st.taddr + 2 * st.bn + st.cl, hprev);
+      } else {
+        load16<WI>(p, p.f0 + (size_t)pix * p.hidden + c, z);
+        load16<WI>(p, hp, hprev);
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float q = tanh_f(y[i]);

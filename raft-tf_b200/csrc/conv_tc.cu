@@ -41,8 +41,9 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
   static constexpr int kAccCols = 2 * BLOCK_N;  // hi*hi | cross terms
-  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
-                                   : (2 * kAccCols <= 256) ? 256 : 512;
+  // two accumulator buffers; tiles of >= 32 columns take all 512 columns: a CTA that owns a single tile (batch 1) parks
+  // the fp32 operands of the gate epilogues behind its one live buffer (Stash, common.cuh) -- up to 3 x BLOCK_N columns
+  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kColsPerWarp = BLOCK_N >= 96 ? 32 : 16;
   static constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1 column groups of epilogue warps
@@ -225,6 +226,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       asm volatile("griddepcontrol.wait;" ::: "memory");  // addend / z / h reads and all stores come after the predecessor
       int li = 0;
       int staged_nt = -1;
+      // ---- operand stash (see common.cuh): single-tile CTAs of the GRU gate convs, while the MMA loop runs ----
+      uint32_t stash_row = 0;
+      if constexpr (!FH2 && !EXTRAS && BLOCK_N >= 32) {
+        const int nops = p.epi == EPI_Q ? 3 : 2;
+        if (p.stash && wide && (p.epi == EPI_ZR || p.epi == EPI_Q) && g.total_tiles <= (int)gridDim.x &&
+            Cfg::kAccCols + nops * BLOCK_N <= Cfg::kTmemCols && first < g.total_tiles) {
+          const int mq = first / g.n_tiles, nt = first - mq * g.n_tiles;
+          const int b = mq / tiles_per_img, trem = mq - b * tiles_per_img;
+          const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
+          const int py = (ty << g.bh_log2) + (r >> g.bw_log2), px = (tx << g.bw_log2) + (r & ((1 << g.bw_log2) - 1));
+          const bool valid = (py < p.h) && (px < p.w) && (mq < g.m_tiles);
+          const int pix = (b * p.h + py) * p.w + px, n0 = nt * BLOCK_N;
+          stash_row = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAccCols;
+#pragma unroll 1
+          for (int cc = 0; cc < Cfg::kColsPerWarp; cc += 16) {
+            const int c = grp * Cfg::kColsPerWarp + cc;
+            if (n0 + c >= p.cout) break;  // warp-uniform
+            float t[16];
+            auto fetch = [&](const float* src) {
+              if (valid) { ld256_nc(src, t); ld256_nc(src + 8, t + 8); }
+              else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = 0.f;
+              }
+            };
+            if (p.addend) { fetch(p.addend + (size_t)pix * p.cout + n0 + c); tmem_st16(stash_row + c, t); }
+            if (p.epi == EPI_ZR) {
+              if (n0 + c >= p.hidden) {  // r half: h (model_utils.py:144,153)
+                fetch(p.f1 + (size_t)pix * p.hidden + (n0 + c - p.hidden));
+                tmem_st16(stash_row + BLOCK_N + c, t);
+              }
+            } else {  // EPI_Q: z and h (model_utils.py:147,155)
+              fetch(p.f0 + (size_t)pix * p.hidden + n0 + c);
+              tmem_st16(stash_row + BLOCK_N + c, t);
+              fetch(p.f1 + (size_t)pix * p.hidden + n0 + c);
+              tmem_st16(stash_row + 2 * BLOCK_N + c, t);
+            }
+          }
+          tmem_st_wait();
+        }
+      }
       for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
         const int mt = PAIR ? 2 * mq + rank : mq;
@@ -291,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           if (!FH2 && valid) {
             if (wide) {
-              epilogue_wide16(p, pix, n0 + c, v);
+              epilogue_wide16(p, pix, n0 + c, v, Stash{stash_row, BLOCK_N, c});
             } else {
               epilogue_store<8>(p, pix, n0 + c, v);
               epilogue_store<8>(p, pix, n0 + c + 8, v + 8);

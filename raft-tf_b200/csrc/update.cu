@@ -120,6 +120,7 @@ struct Workspace {
   float* H;
   float* Z;
   float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
+  float* pre_h;   // RAFT_B200_ZR1_SIDE: pre[0] + conv over the `h` channels of zr1 (computed beside the motion encoder)
   unsigned int* counters;  // grid-barrier counters of the fused update-step kernel (update_fused.cu)
   float* fh2_part;         // [npix][kFh2MaxParts][18]: per-pixel partial products of the folded flow_head/conv2 (EPI_FH2)
   size_t total;
@@ -154,6 +155,11 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
       W.pre[i] = reinterpret_cast<float*>(b + off);
       off += align_up(npix * (size_t)((i & 1) ? v.hidden : 2 * v.hidden) * sizeof(float), 1024);
     }
+  }
+  W.pre_h = nullptr;
+  if (!v.small) {
+    W.pre_h = reinterpret_cast<float*>(b + off);
+    off += align_up(npix * (size_t)(2 * v.hidden) * sizeof(float), 1024);
   }
   W.counters = reinterpret_cast<unsigned int*>(b + off);
   off += 1024;
@@ -552,8 +558,8 @@ static void set_act(ConvParams& p, int act, SplitPtr d0, int stride0, int choff0
 // At batch 1 a conv uses 55-110 of the 148 SMs, so the two branches genuinely overlap.  Fork/join with
 // events is also how the branch is expressed inside a CUDA-graph capture.
 struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
   int device = -1;
 };
 static int side_stream(SideStream** out) {
@@ -564,6 +570,8 @@ static int side_stream(SideStream** out) {
     RB_CHECK_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
     RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
     RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    RB_CHECK_CUDA(cudaStreamCreateWithFlags(&ss.stream2, cudaStreamNonBlocking));
+    RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming));
     ss.device = dev;
   }
   *out = &ss;
@@ -599,6 +607,22 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   if ((rc = side_stream(&ss))) return rc;
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  // RAFT_B200_ZR1_SIDE=1 (experiment): the `h` channels of the first GRU conv (z|r, 1x5) depend only on the state the
+  // previous iteration left, not on this iteration's motion features, so their half of the K loop (10 of 20 k-iterations)
+  // can run on a second forked stream beside lookup / motion encoder (<= 38 CTAs: the SMs the batch-1 convs leave idle) and
+  // reach the conv as its fp32 addend.  Same arithmetic, different fp32 summation order.
+  static const bool zr1_side_env = getenv("RAFT_B200_ZR1_SIDE") != nullptr;
+  const bool zr1_side = zr1_side_env && !fused && can_hoist(v) && math_mode() == RB_MATH_TC && !g_dbg;
+  if (zr1_side) {
+    RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream2, ss->fork, 0));
+    ConvParams p = base_params(v, L, blob, P_ZR1, W.hx, v.hx, 0, B, h, w);
+    p.ck_begin = 0; p.ck_count = v.hidden / 64; p.ck_skip_at = 1 << 20; p.ck_skip = 0;
+    p.bias = nullptr; p.addend = W.pre[0];
+    p.epi = EPI_F32; p.f0 = W.pre_h; p.scale = 1.f;
+    p.cta_limit = (long)B * h * w <= 16384 ? 38 : 0;
+    if ((rc = launch_conv(p, ss->stream2))) return rc;
+    RB_CHECK_CUDA(cudaEventRecord(ss->join2, ss->stream2));
+  }
   {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
     static const int seg_env = getenv("RAFT_B200_CONV7_SEG") ? atoi(getenv("RAFT_B200_CONV7_SEG")) : 0;  // tuning knob
     const int seg = seg_env ? seg_env : ((long)B * h * w <= 16384 ? 16 : 32);  // same-box A/B at 55x128: 792 / 772 / 781 us per 4 iterations for 32 / 16 / 8
@@ -685,12 +709,18 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     int zr = pass == 0 ? P_ZR1 : P_ZR2, q = pass == 0 ? P_Q1 : P_Q2;
     ConvParams p = base_params(v, L, blob, zr, W.hx, v.hx, 0, B, h, w);
     hoist_inp(v, W, pass * 2 + 0, p);
-    p.epi = EPI_ZR; p.f0 = W.Z; p.f1 = W.H;
+    if (pass == 0 && zr1_side) {  // only the motion / flow channels are left for the main conv
+      p.ck_begin = (v.hidden + v.ctx) / 64; p.ck_count = v.hx / 64 - p.ck_begin; p.ck_skip_at = 1 << 20; p.ck_skip = 0;
+      p.addend = W.pre_h;
+      RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join2, 0));
+    }
+    static const int stash = getenv("RAFT_B200_NO_STASH") ? 0 : 1;  // A/B knob (common.cuh: Stash)
+    p.epi = EPI_ZR; p.f0 = W.Z; p.f1 = W.H; p.stash = stash;
     p.d0_hi = W.qx.hi; p.d0_lo = W.qx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
     if ((rc = launch_conv_dbg(p, s))) return rc;
     p = base_params(v, L, blob, q, W.qx, v.hx, 0, B, h, w);
     hoist_inp(v, W, pass * 2 + 1, p);
-    p.epi = EPI_Q; p.f0 = W.Z; p.f1 = W.H;
+    p.epi = EPI_Q; p.f0 = W.Z; p.f1 = W.H; p.stash = stash;
     p.d0_hi = W.hx.hi; p.d0_lo = W.hx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
     if ((rc = launch_conv_dbg(p, s))) return rc;
   }

@@ -5,7 +5,12 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out
 echo "== pytest -m gpu"
-timeout 1500 python -m pytest tests -q -m gpu --timeout 900 -x 2>&1 | tail -15 | tee $O/pytest_gpu.log
+# one process per file: a device-side trap poisons the CUDA context of its process only
+: > $O/pytest_gpu.log
+for f in tests/test_gpu_kernels.py tests/test_gpu_e2e.py tests/test_gpu_fullsize.py tests/test_gpu_configs.py tests/test_gpu_variants.py tests/test_gpu_multi.py; do
+  echo "-- $f" | tee -a $O/pytest_gpu.log
+  timeout 900 python -m pytest $f -q -m gpu --timeout 600 --maxfail=4 -s 2>&1 | grep -vE "^\s*$" | tail -25 | tee -a $O/pytest_gpu.log
+done
 echo "== bench (ours)"
 timeout 900 python bench.py 2>$O/bench_err.log | tail -1 | tee $O/bench_default.json | cut -c1-1500
 echo "== bench (reference arm, 2 steps)"
@@ -21,7 +26,10 @@ for B in 1 8; do
   done
 done 2>&1 | tee $O/lookup_ab.log
 echo "== stage timings"
-for w in corr encoder update iterate; do timeout 200 python tools/micro.py $w 2>&1 | tail -1; done | tee $O/stages.log
+for w in corr encoder update iterate forward; do timeout 200 python tools/micro.py $w 2>&1 | tail -1; done | tee $O/stages.log
+echo -n "no FH2 fuse: "; RAFT_B200_NO_FH2_FUSE=1 timeout 200 python tools/micro.py update 2>&1 | tail -1 | tee -a $O/stages.log
+echo -n "no FH2 fuse: "; RAFT_B200_NO_FH2_FUSE=1 timeout 200 python tools/micro.py iterate 2>&1 | tail -1 | tee -a $O/stages.log
+echo -n "volume-free forward: "; RAFT_B200_VOLUME_FREE=1 timeout 200 python tools/micro.py forward 2>&1 | tail -1 | tee -a $O/stages.log
 timeout 200 python tools/micro.py corr --flush 2>&1 | tail -1 | tee -a $O/stages.log
 echo "== ncu launch list (one forward, no graph)"
 RAFT_B200_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file $O/r02_launches.csv \
@@ -35,6 +43,6 @@ echo "== ncu full: corr build (level-0 GEMM + the rest)"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|split_rows|pool_fmap" -s 12 -c 12 -f -o $O/r02_corr \
     python tools/micro.py corr --reps 1 --n 1 > $O/ncu_corr.log 2>&1
 echo "== ncu full: update-step convs"
-RAFT_B200_NO_PDL=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|flow_conv7" -s 15 -c 11 -f -o $O/r02_update \
+RAFT_B200_NO_PDL=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|flow_conv7|fh2_gather" -s 15 -c 11 -f -o $O/r02_update \
     python tools/micro.py update --reps 2 --n 1 > $O/ncu_update.log 2>&1
 ls -la $O | tail -12
