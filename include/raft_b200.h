@@ -138,7 +138,7 @@ int rb_raft_iterate(int small, const void* weights, void* workspace, const float
  * iteration evaluates only the (2r+3) x (2r+3) entries per pixel and level that the bilinear taps can touch, as fp32
  * dot products against the pooled feature maps, and applies the same tap arithmetic as rb_corr_lookup.  Results equal
  * the materialised path up to the summation order / operand rounding of the dot products (parity is on the flow, 1e-3).
- * rb_corr_otf_prepare pools fmap2 once per pair into `workspace` (levels 1..3, fp32); C <= 256, multiple of 4. */
+ * rb_corr_otf_prepare pools fmap2 once per pair into `workspace` (levels 1..3, fp32); C = 128 or 256. */
 int rb_corr_otf_workspace_bytes(int B, int h, int w, int C, size_t* bytes);
 int rb_corr_otf_prepare(const float* fmap2, void* workspace, size_t workspace_bytes, int B, int h, int w, int C,
                         void* stream);

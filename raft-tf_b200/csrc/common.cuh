@@ -401,8 +401,11 @@ struct Stash {
 };
 
 // WI: compile the RAFT_B200_WHATIF hooks in (fused kernel only; everything the default path runs stays lean)
+// `live` = this lane's pixel exists.  Without a stash the caller only calls live lanes; WITH a stash every lane of the warp
+// must come here (tcgen05.ld is .sync.aligned: warp-collective) and dead lanes skip the global accesses.
 template <bool WI = false>
-__device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, int c, float* y, const Stash st = Stash{0, 0, 0}) {
+__device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, int c, float* y, const Stash st = Stash{0, 0, 0},
+                                                const bool live = true) {
   if (p.bias) {
     float t[16];
     ld256_nc(p.bias + c, t);
@@ -446,7 +449,7 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
       if (c < p.hidden) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = sigmoid_f(y[i]);
-        store16<WI>(p, p.f0 + (size_t)pix * p.hidden + c, y);
+        if (live) store16<WI>(p, p.f0 + (size_t)pix * p.hidden + c, y);
       } else {
         const int ch = c - p.hidden;
         float hprev[16];
@@ -454,7 +457,7 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
         else load16<WI>(p, p.f1 + (size_t)pix * p.hidden + ch, hprev);
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = sigmoid_f(y[i]) * hprev[i];
-        store_split16<WI>(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + ch, y);
+        if (live) store_split16<WI>(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + ch, y);
       }
     } break;
     case EPI_Q: {
@@ -472,8 +475,10 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
         const float q = tanh_f(y[i]);
         y[i] = (1.0f - z[i]) * hprev[i] + z[i] * q;  // model_utils.py:147,155,168
       }
-      store16<WI>(p, hp, y);
-      store_split16<WI>(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + c, y);
+      if (live) {
+        store16<WI>(p, hp, y);
+        store_split16<WI>(p, p.d0_hi, p.d0_lo, (size_t)pix * p.d0_stride + p.d0_choff + c, y);
+      }
     } break;
     default: {  // EPI_F32
       if (p.act == ACT_RELU) {

@@ -331,9 +331,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               acc2[16] = fmaf(y, w4.x, acc2[16]); acc2[17] = fmaf(y, w4.y, acc2[17]);
             }
           }
-          if (!FH2 && valid) {
+          if (!FH2 && (valid || stash_row != 0)) {  // with a stash the TMEM reads inside are warp-collective: all lanes go
             if (wide) {
-              epilogue_wide16(p, pix, n0 + c, v, Stash{stash_row, BLOCK_N, c});
+              epilogue_wide16(p, pix, n0 + c, v, Stash{stash_row, BLOCK_N, c}, valid);
             } else {
               epilogue_store<8>(p, pix, n0 + c, v);
               epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
@@ -411,12 +411,11 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   const CUtensorMapDataType dt = kind == TMAP_F16_SW128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const CUtensorMapSwizzle sw = kind == TMAP_F32_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                : kind == TMAP_F32_PLAIN ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B;
-  // L2 promotion: 256-byte requests suit the dense 128-byte operand rows of the GEMM tiles; the lookup's 48-byte patch
+  const CUtensorMapSwizzle sw = kind == TMAP_F16_SW128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // L2 promotion: 256-byte requests suit the dense 128-byte operand rows of the GEMM tiles; the lookup's 64-byte patch
   // rows are a gather (r01: 1.86x the algorithmic DRAM bytes) -> none.  RAFT_B200_LOOKUP_L2PROMO = 0/64/128/256: A/B knob.
   CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  if (kind == TMAP_F32_PLAIN) {
+  if (kind == TMAP_F32_SW64_GATHER) {
     static const int env = getenv("RAFT_B200_LOOKUP_L2PROMO") ? atoi(getenv("RAFT_B200_LOOKUP_L2PROMO")) : 0;
     promo = env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
             : env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;

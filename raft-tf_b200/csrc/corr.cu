@@ -283,14 +283,17 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
 // L2 requests).  v5:
 //   * one WARP per query pixel, its 4 pyramid levels = 4 units; lane = tap (t = i*D + j, ceil(K/32) rounds), so the
 //     results of a unit are 32 consecutive words of the staging row (conflict-free) and a unit's patch is read by
-//     lanes whose rows differ by a 12-word pitch (8 distinct bank groups: conflict-free up to j = 0 / D-1);
-//   * the patch of a unit is ONE TMA box of 12 columns x (2r+2) rows fp32 starting at the UNALIGNED origin
-//     (x0, y0) = clamp(trunc(centroid - r)) -- no swizzle, 48-byte rows, L2 promotion off: per row 76 B of sectors on
-//     average instead of 80-112, and one row less.  The (2r+2)^2 footprint plus the fp32-rounding slack column fits;
-//     a unit whose rounding slack falls outside the box (trunc(fl(c+d)) == trunc(c-r)+d+1 in the last row) is detected
-//     while its index tables are built and takes a per-tap global-load path (warp-uniform branch, ~never taken);
-//   * separable index math once per unit: x table {qx, 1-qx, byte offset of x0, of x1} and y table {qy, 1-qy, row offset
-//     of y0, of y1} in shared memory (two 128-bit broadcast loads per tap), tap arithmetic exactly as the reference
+//     lanes whose rows land in 8 distinct bank groups under the 64-byte swizzle (conflict-free up to j = 0 / D-1);
+//   * the patch of a unit is ONE TMA box of 16 columns x (2r+2) rows fp32 (64-byte swizzle, L2 promotion off) whose origin
+//     is (x0 & ~3, y0), (x0, y0) = clamp(trunc(centroid - r)): one row less than v4.  (A 12-column box at the unaligned x0
+//     was the first r02 attempt: the TMA unit raises "illegal instruction" when the innermost box coordinate is not a
+//     multiple of 16 bytes -- compute-sanitizer log in profiles/r02_notes.md.)  The (2r+2)^2 footprint plus the
+//     fp32-rounding slack column fits; a unit whose rounding slack falls outside the box (trunc(fl(c+d)) ==
+//     trunc(c-r)+d+1 in the last row) is detected while its index tables are built and takes a per-tap global-load
+//     path (warp-uniform branch, ~never taken);
+//   * separable index math once per unit: x table {qx, 1-qx, 4*col of x0, of x1} and y table {qy, 1-qy, swizzled row address
+//     of y0, of y1} in shared memory (two 128-bit broadcast loads per tap; texel address = row address XOR 4*col, one
+//     LOP3), tap arithmetic exactly as the reference
 //     (trunc toward zero, clamp, weights from the CLAMPED x1/y1, add_n order, no FMA contraction) => bit-identical;
 //   * every warp is self-contained (own mbarrier, own staging row, __syncwarp only): no block-wide barrier after the
 //     prologue; the fp16 hi/lo split happens in the output pass on 8 consecutive channels per lane (128-bit stores).
@@ -298,7 +301,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
 template <int R, bool OTF = false>
 struct LookupV5 {
   // OTF (volume-free): the patch is COMPUTED (dot products against pooled fmap2), with the slack row included
-  static constexpr int D = 2 * R + 1, K = D * D, COLS = 12, ROWS = OTF ? D + 2 : D + 1, PITCH = COLS * 4;
+  static constexpr int D = 2 * R + 1, K = D * D, COLS = 16, ROWS = OTF ? D + 2 : D + 1, PITCH = COLS * 4;
   static constexpr int SLOT = (ROWS * PITCH + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
   static constexpr int PB = 16, WARPS = PB, NT = WARPS * 32, ROUNDS = (K + 31) / 32;
   static constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel (324 -> 328, 196 -> 200)
@@ -306,8 +309,7 @@ struct LookupV5 {
   static constexpr int kTabOff = PB * 4 * SLOT;
   static constexpr int kStageOff = kTabOff + PB * 4 * TABN * 16;
   static constexpr int kBarOff = kStageOff + PB * OUTP * 4;
-  static constexpr int kF1Off = kBarOff + 128;  // OTF: fmap1 row of each warp's pixel, [PB][C <= 256] fp32
-  static constexpr int kBytes = kF1Off + (OTF ? PB * 256 * 4 : 0);
+  static constexpr int kBytes = kBarOff + 128;
 };
 // volume-free mode: level l of the pyramid is fmap1 . pool^l(fmap2)^T / sqrt(C) (exact by linearity, gemm_tc.cu); here the
 // (2r+3) x 11 entries a unit can touch are evaluated on the fly instead of being read from a materialised volume.
@@ -317,8 +319,12 @@ struct OtfView {
   int C, N;                        // channels (<= 256, multiple of 4), pixels per sample (h*w)
 };
 struct PyramidMapsV5 {
-  CUtensorMap m[RB_NUM_LEVELS];  // (W_l, H_l, B*N) fp32, box (12, 2r+2, 1), no swizzle, no L2 promotion
+  CUtensorMap m[RB_NUM_LEVELS];  // (W_l, H_l, B*N) fp32, box (16, 2r+2, 1), 64-byte swizzle, no L2 promotion
 };
+// Byte offset of patch element (row, col) inside a unit whose slot starts `unit_off` bytes after the 1024-byte aligned
+// start of shared memory: rows are 64 bytes; CU_TENSOR_MAP_SWIZZLE_64B XORs the 16-byte chunk index with bits [7,9) of the
+// shared-memory byte address, i.e. with s(row) = (unit_off / 128 + row / 2) & 3.
+__device__ __forceinline__ int v5_row_off(int unit_off, int row) { return row * 64 + ((((unit_off >> 7) + (row >> 1)) & 3) << 4); }
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
@@ -327,7 +333,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 }
 
 template <int R, bool SPLIT, bool OTF = false>
-__global__ void __launch_bounds__(LookupV5<R, OTF>::NT, 3)
+__global__ void __launch_bounds__(LookupV5<R, OTF>::NT, OTF ? 2 : 3)
 corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMapsV5 maps,
                       const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
                       __half* __restrict__ out_lo, int out_stride, int npix, const OtfView otf) {
@@ -343,7 +349,8 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
   // kernel (per-warp barriers) died with "illegal instruction" on the B200 -- not worth the ~1 us of decoupling.
   uint64_t* bar = reinterpret_cast<uint64_t*>(lk5_smem + L::kBarOff);
   uint8_t* patch = lk5_smem + warp * 4 * L::SLOT;
-  const uint32_t patch_u32 = tc::smem_u32(patch);
+  const uint32_t patch0_u32 = tc::smem_u32(lk5_smem);  // 1024-byte aligned (checked below): slot offsets decide the swizzle
+  if (threadIdx.x == 0 && (patch0_u32 & 1023u)) __trap();
   const bool live = pix < npix;
 
   int n_tma = 0;
@@ -381,6 +388,7 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     const int H = pv.hl[k], W = pv.wl[k];
     bx = min(max((int)__fadd_rn(c.x * inv, (float)(-R)), 0), W - 1);
     by = min(max((int)__fadd_rn(c.y * inv, (float)(-R)), 0), H - 1);
+    if (!OTF) bx &= ~3;  // TMA: the innermost box coordinate must be a multiple of 16 bytes
     if (!OTF && lane < 4 && pv.tma_ok[k]) tc::tma_load_3d(&maps.m[k], bar, patch + k * L::SLOT, bx, by, pix);
   }
   // ---- index tables: lane -> (unit k = lane >> 3, entry e = lane & 7); entry 8 (r = 4) by the lanes with e = 0 / 1 ------
@@ -411,7 +419,9 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
       const float qy = __fsub_rn((float)y1, y);  // utils.py:85
       const int r0 = y0 - byk, r1 = y1 - byk;
       if ((unsigned)r0 >= (unsigned)L::ROWS || (unsigned)r1 >= (unsigned)L::ROWS) bad = 1;
-      tab[k * L::TABN + D + j] = make_float4(qy, __fsub_rn(1.0f, qy), __int_as_float(r0 * L::PITCH), __int_as_float(r1 * L::PITCH));
+      const int uoff = (warp * 4 + k) * L::SLOT;  // slot offset from the 1024-byte aligned start of shared memory
+      tab[k * L::TABN + D + j] = make_float4(qy, __fsub_rn(1.0f, qy), __int_as_float((int)patch0_u32 + uoff + v5_row_off(uoff, r0)),
+                                             __int_as_float((int)patch0_u32 + uoff + v5_row_off(uoff, r1)));
     };
     if (e < D) { x_entry(e); y_entry(e); }
     if (D > 8) {
@@ -420,29 +430,69 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     }
   }
   const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);  // bits 8k..8k+7 belong to unit k
-  // ---- volume-free mode: evaluate the patch entries -- lane = entry (row, col), sequential fp32 dot product over C ------
+  // ---- volume-free mode: evaluate the patch entries ----------------------------------------------------------------------
+  // The warp reads each target feature row COALESCED (lane = 4 channels per 128-channel half; fmap1[pix] stays in 8
+  // registers), 8 entries at a time, and reduces the 8 x 32 partial sums with a recursive-halving exchange (9 shuffles per 8
+  // entries).  First version (lane = entry, each lane streaming its own 1 KB row): 32 L1 lines per load instruction, 2x
+  // sector waste, 1.3 ms per lookup at 55x128 -- L2-bound; neighbouring pixels share most rows, which this form lets L1 see.
   if constexpr (OTF) {
-    float* f1s = reinterpret_cast<float*>(lk5_smem + L::kF1Off) + warp * 256;
     const int C = otf.C;
-    for (int ch = lane * 4; ch < C; ch += 128)
-      *reinterpret_cast<float4*>(f1s + ch) = __ldg(reinterpret_cast<const float4*>(otf.f1 + (size_t)pix * C + ch));
-    __syncwarp();
+    const bool two = C > 128;  // C is 128 or 256 (launch_lookup_otf)
+    const float4 fa = __ldg(reinterpret_cast<const float4*>(otf.f1 + (size_t)pix * C + 4 * lane));
+    const float4 fb = two ? __ldg(reinterpret_cast<const float4*>(otf.f1 + (size_t)pix * C + 128 + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int b = pix / otf.N;
     const float sq = sqrtf((float)C);
+    constexpr int NE = L::ROWS * 11;  // columns 0..10 (= D+1 + rounding slack at r = 4) can be indexed
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
       const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
       const int H = pv.hl[k], W = pv.wl[k];
-      for (int e = lane; e < L::ROWS * 11; e += 32) {  // columns 0..10 (= D+1 + rounding slack at r = 4) can be indexed
-        const int row = e / 11, col = e - row * 11;
-        const float* f2 = otf.f2[k] + (((size_t)b * H + min(byk + row, H - 1)) * W + min(bxk + col, W - 1)) * C;
-        float acc = 0.f;
-        for (int ch = 0; ch < C; ch += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(f1s + ch);
-          const float4 v = __ldg(reinterpret_cast<const float4*>(f2 + ch));
-          acc = fmaf(a.x, v.x, acc); acc = fmaf(a.y, v.y, acc); acc = fmaf(a.z, v.z, acc); acc = fmaf(a.w, v.w, acc);
+      const float* f2b = otf.f2[k] + (size_t)b * H * W * C + 4 * lane;
+#pragma unroll 1
+      for (int e0 = 0; e0 < NE; e0 += 8) {
+        float p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = min(e0 + u, NE - 1);
+          const int row = e / 11, col = e - row * 11;
+          const float* src = f2b + ((size_t)min(byk + row, H - 1) * W + min(bxk + col, W - 1)) * C;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+          float acc = fmaf(fa.w, v.w, fmaf(fa.z, v.z, fmaf(fa.y, v.y, fa.x * v.x)));
+          if (two) {
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(src + 128));
+            acc = fmaf(fb.w, v2.w, fmaf(fb.z, v2.z, fmaf(fb.y, v2.y, fmaf(fb.x, v2.x, acc))));
+          }
+          p[u] = acc;
         }
-        *reinterpret_cast<float*>(patch + k * L::SLOT + row * L::PITCH + col * 4) = __fdiv_rn(acc, sq);  // divide AFTER the matmul (:213)
+        {  // 8 -> 4 -> 2 -> 1 values per lane (partners at xor 16, 8, 4), then the last two steps of a plain butterfly
+          const bool up = (lane & 16) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float keep = up ? p[i + 4] : p[i], send = up ? p[i] : p[i + 4];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+        }
+        {
+          const bool up = (lane & 8) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float keep = up ? p[i + 2] : p[i], send = up ? p[i] : p[i + 2];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+        }
+        {
+          const bool up = (lane & 4) != 0;
+          const float keep = up ? p[1] : p[0], send = up ? p[0] : p[1];
+          p[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        p[0] += __shfl_xor_sync(0xffffffffu, p[0], 2);
+        p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+        const int e = e0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if ((lane & 3) == 0 && e < NE) {
+          const int row = e / 11, col = e - row * 11;
+          const int uoff = (warp * 4 + k) * L::SLOT;
+          *reinterpret_cast<float*>(lk5_smem + uoff + (v5_row_off(uoff, row) ^ (col * 4))) = __fdiv_rn(p[0], sq);  // divide AFTER the matmul (:213)
+        }
       }
     }
   }
@@ -453,14 +503,15 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
       if (pv.tma_ok[k]) continue;
       const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);
       const int H = pv.hl[k], W = pv.wl[k];
-      for (int e = lane; e < L::ROWS * 3; e += 32) {
-        const int row = e / 3, ch = e - row * 3;
+      const int uoff = (warp * 4 + k) * L::SLOT;
+      for (int e = lane; e < L::ROWS * 4; e += 32) {
+        const int row = e >> 2, ch = e & 3;
         const float* src = pv.base[k] + ((size_t)pix * H + min(byk + row, H - 1)) * W;
         const int col = bxk + ch * 4;
         float4 v;
         v.x = __ldg(src + min(col + 0, W - 1)); v.y = __ldg(src + min(col + 1, W - 1));
         v.z = __ldg(src + min(col + 2, W - 1)); v.w = __ldg(src + min(col + 3, W - 1));
-        *reinterpret_cast<float4*>(patch + k * L::SLOT + row * L::PITCH + ch * 16) = v;
+        *reinterpret_cast<float4*>(lk5_smem + uoff + (v5_row_off(uoff, row) ^ (ch * 16))) = v;
       }
     }
   }
@@ -472,7 +523,6 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
     const int bxk = __shfl_sync(0xffffffffu, bx, k), byk = __shfl_sync(0xffffffffu, by, k);  // converged here (slow path only)
     const float4* xt = tab + k * L::TABN;
     const float4* yt = xt + D;
-    const uint32_t pb = patch_u32 + k * L::SLOT;
     const bool slow = ((badmask >> (8 * k)) & 0xffu) != 0;  // warp-uniform
 #pragma unroll
     for (int rd = 0; rd < L::ROUNDS; ++rd) {
@@ -483,13 +533,14 @@ corr_lookup_v5_kernel(const __grid_constant__ PyramidView pv, const __grid_const
         const float wc = __fmul_rn(X.y, Y.x), wd = __fmul_rn(X.y, Y.y);
         const int a0 = __float_as_int(X.z), a1 = __float_as_int(X.w), r0 = __float_as_int(Y.z), r1 = __float_as_int(Y.w);
         float Ia, Ib, Ic, Id;
-        if (OTF || !slow) {
-          Ia = lds_f32(pb + r0 + a0); Ib = lds_f32(pb + r1 + a0);
-          Ic = lds_f32(pb + r0 + a1); Id = lds_f32(pb + r1 + a1);
+        if (OTF || !slow) {  // r0 / r1: swizzled row addresses (64-byte aligned + chunk phase), a0 / a1: 4 * column
+          Ia = lds_f32(r0 ^ a0); Ib = lds_f32(r1 ^ a0);
+          Ic = lds_f32(r0 ^ a1); Id = lds_f32(r1 ^ a1);
         } else {  // rounding slack outside the box: read the four texels from the volume itself
           const int H = pv.hl[k], W = pv.wl[k];
           const float* img = pv.base[k] + (size_t)pix * H * W;
-          const int x0 = bxk + (a0 >> 2), x1 = bxk + (a1 >> 2), y0 = byk + r0 / L::PITCH, y1 = byk + r1 / L::PITCH;
+          const int ubase = (int)patch0_u32 + (warp * 4 + k) * L::SLOT;
+          const int x0 = bxk + (a0 >> 2), x1 = bxk + (a1 >> 2), y0 = byk + ((r0 - ubase) >> 6), y1 = byk + ((r1 - ubase) >> 6);
           Ia = __ldg(img + (size_t)y0 * W + x0); Ib = __ldg(img + (size_t)y1 * W + x0);
           Ic = __ldg(img + (size_t)y0 * W + x1); Id = __ldg(img + (size_t)y1 * W + x1);
         }
@@ -640,8 +691,8 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
       if (!pv.tma_ok[l]) continue;
       uint64_t dims[3] = {(uint64_t)pv.wl[l], (uint64_t)pv.hl[l], (uint64_t)npix};
       uint64_t str[2] = {(uint64_t)pv.wl[l] * 4, (uint64_t)pv.wl[l] * pv.hl[l] * 4};
-      uint32_t box[3] = {12u, (uint32_t)(2 * radius + 2), 1};
-      if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_PLAIN) != RB_OK) pv.tma_ok[l] = 0;  // plain loads
+      uint32_t box[3] = {16u, (uint32_t)(2 * radius + 2), 1};
+      if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_SW64_GATHER) != RB_OK) pv.tma_ok[l] = 0;  // plain loads
     }
     static const bool no_tma = getenv("RAFT_B200_LOOKUP_NOTMA") != nullptr;  // diagnostic: stage every level with plain loads
     if (no_tma)
@@ -689,7 +740,7 @@ __global__ void otf_pool_kernel(const float* __restrict__ src, float* __restrict
 int launch_lookup_otf(const float* fmap1, const float* fmap2, const float* pooled, const float* coords, float* out_f32,
                       __half* out_hi, __half* out_lo, int out_stride, int B, int h, int w, int C, int radius, cudaStream_t s) {
   RB_REQUIRE(radius == 3 || radius == 4, RB_ERR_UNSUPPORTED, "radius %d unsupported", radius);
-  RB_REQUIRE(C > 0 && C <= 256 && C % 4 == 0, RB_ERR_BAD_SHAPE, "volume-free lookup: C=%d (need a multiple of 4, <= 256)", C);
+  RB_REQUIRE(C == 128 || C == 256, RB_ERR_BAD_SHAPE, "volume-free lookup: C=%d (128 = raft-small, 256 = raft-things)", C);
   RB_REQUIRE((h >> 3) >= 1 && (w >> 3) >= 1, RB_ERR_BAD_SHAPE, "volume-free lookup: grid %dx%d too small for 4 levels", h, w);
   RB_REQUIRE(out_hi == nullptr || out_stride % 8 == 0, RB_ERR_BAD_SHAPE, "lookup: split output stride %d", out_stride);
   PyramidView pv;

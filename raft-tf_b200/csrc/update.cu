@@ -120,7 +120,6 @@ struct Workspace {
   float* H;
   float* Z;
   float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
-  float* pre_h;   // RAFT_B200_ZR1_SIDE: pre[0] + conv over the `h` channels of zr1 (computed beside the motion encoder)
   unsigned int* counters;  // grid-barrier counters of the fused update-step kernel (update_fused.cu)
   float* fh2_part;         // [npix][kFh2MaxParts][18]: per-pixel partial products of the folded flow_head/conv2 (EPI_FH2)
   size_t total;
@@ -155,11 +154,6 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
       W.pre[i] = reinterpret_cast<float*>(b + off);
       off += align_up(npix * (size_t)((i & 1) ? v.hidden : 2 * v.hidden) * sizeof(float), 1024);
     }
-  }
-  W.pre_h = nullptr;
-  if (!v.small) {
-    W.pre_h = reinterpret_cast<float*>(b + off);
-    off += align_up(npix * (size_t)(2 * v.hidden) * sizeof(float), 1024);
   }
   W.counters = reinterpret_cast<unsigned int*>(b + off);
   off += 1024;
@@ -465,31 +459,39 @@ static int launch_flow_head2(const ConvParams& p, cudaStream_t s) {
 // G[q][s][tap*2+o] = sum over the part's channels of relu(conv1)[q][c] * W2[tap][c][o].  The 3x3 conv (SAME: zero outside
 // the image) is then  delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o]  -- fixed summation order
 // (tap-major, parts ascending): bit-reproducible, batched == per-sample.  coords1 += delta (RAFT.py:102).
-__global__ void __launch_bounds__(64) fh2_gather_kernel(const float* __restrict__ part, int parts, const float* __restrict__ bias,
-                                                        float* coords1, float* delta_out, int B, int h, int w) {
+// One WARP per pixel: the 9 * parts partial pairs are spread over the lanes (item = tap * parts + part), each lane sums its
+// items in ascending order and a fixed xor butterfly finishes the sum.  (First version: one thread per pixel walking 72
+// dependent-latency loads -- 11 us per launch in the r02 ncu list for 4 MB of L2-resident data.)
+__global__ void __launch_bounds__(256) fh2_gather_kernel(const float* __restrict__ part, int parts, const float* __restrict__ bias,
+                                                         float* coords1, float* delta_out, int B, int h, int w) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * h * w) return;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= B * h * w) return;  // warp-uniform
   const int x = i % w, y = (i / w) % h, b = i / (w * h);
   float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
+  for (int it = lane; it < 9 * parts; it += 32) {
+    const int t = it / parts, s = it - t * parts;
     const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-    if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-    const float* g = part + ((size_t)((b * h + yy) * w + xx) * parts) * 18 + t * 2;
-    for (int s = 0; s < parts; ++s) {
-      const float2 v = *reinterpret_cast<const float2*>(g + s * 18);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {  // SAME padding: conv1's activations are zero outside the image
+      const float2 v = __ldg(reinterpret_cast<const float2*>(part + ((size_t)((b * h + yy) * w + xx) * parts + s) * 18 + t * 2));
       d0 += v.x;
       d1 += v.y;
     }
   }
-  d0 += bias[0];
-  d1 += bias[1];
-  float2 c = *reinterpret_cast<float2*>(coords1 + (size_t)i * 2);
-  c.x += d0; c.y += d1;
-  *reinterpret_cast<float2*>(coords1 + (size_t)i * 2) = c;
-  if (delta_out) *reinterpret_cast<float2*>(delta_out + (size_t)i * 2) = make_float2(d0, d1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+  }
+  if (lane == 0) {
+    d0 += bias[0];
+    d1 += bias[1];
+    float2 c = *reinterpret_cast<float2*>(coords1 + (size_t)i * 2);
+    c.x += d0; c.y += d1;
+    *reinterpret_cast<float2*>(coords1 + (size_t)i * 2) = c;
+    if (delta_out) *reinterpret_cast<float2*>(delta_out + (size_t)i * 2) = make_float2(d0, d1);
+  }
 }
 
 static int launch_fh2_gather(const float* part, int parts, const float* bias, float* coords1, float* delta_out, int B, int h,
@@ -497,8 +499,8 @@ static int launch_fh2_gather(const float* part, int parts, const float* bias, fl
   static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((B * h * w + 63) / 64);
-  cfg.blockDim = dim3(64);
+  cfg.gridDim = dim3((B * h * w + 7) / 8);
+  cfg.blockDim = dim3(256);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -558,20 +560,20 @@ static void set_act(ConvParams& p, int act, SplitPtr d0, int stride0, int choff0
 // At batch 1 a conv uses 55-110 of the 148 SMs, so the two branches genuinely overlap.  Fork/join with
 // events is also how the branch is expressed inside a CUDA-graph capture.
 struct SideStream {
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
   int device = -1;
 };
 static int side_stream(SideStream** out) {
-  static thread_local SideStream ss;
+  static thread_local SideStream per_dev[16];  // one set of streams / events per (calling thread, device ordinal)
   int dev = 0;
   RB_CHECK_CUDA(cudaGetDevice(&dev));
+  RB_REQUIRE(dev >= 0 && dev < 16, RB_ERR_UNSUPPORTED, "device ordinal %d (the side streams are kept for ordinals 0..15)", dev);
+  SideStream& ss = per_dev[dev];
   if (ss.device != dev) {
     RB_CHECK_CUDA(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
     RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
     RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
-    RB_CHECK_CUDA(cudaStreamCreateWithFlags(&ss.stream2, cudaStreamNonBlocking));
-    RB_CHECK_CUDA(cudaEventCreateWithFlags(&ss.join2, cudaEventDisableTiming));
     ss.device = dev;
   }
   *out = &ss;
@@ -607,22 +609,6 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   if ((rc = side_stream(&ss))) return rc;
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-  // RAFT_B200_ZR1_SIDE=1 (experiment): the `h` channels of the first GRU conv (z|r, 1x5) depend only on the state the
-  // previous iteration left, not on this iteration's motion features, so their half of the K loop (10 of 20 k-iterations)
-  // can run on a second forked stream beside lookup / motion encoder (<= 38 CTAs: the SMs the batch-1 convs leave idle) and
-  // reach the conv as its fp32 addend.  Same arithmetic, different fp32 summation order.
-  static const bool zr1_side_env = getenv("RAFT_B200_ZR1_SIDE") != nullptr;
-  const bool zr1_side = zr1_side_env && !fused && can_hoist(v) && math_mode() == RB_MATH_TC && !g_dbg;
-  if (zr1_side) {
-    RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream2, ss->fork, 0));
-    ConvParams p = base_params(v, L, blob, P_ZR1, W.hx, v.hx, 0, B, h, w);
-    p.ck_begin = 0; p.ck_count = v.hidden / 64; p.ck_skip_at = 1 << 20; p.ck_skip = 0;
-    p.bias = nullptr; p.addend = W.pre[0];
-    p.epi = EPI_F32; p.f0 = W.pre_h; p.scale = 1.f;
-    p.cta_limit = (long)B * h * w <= 16384 ? 38 : 0;
-    if ((rc = launch_conv(p, ss->stream2))) return rc;
-    RB_CHECK_CUDA(cudaEventRecord(ss->join2, ss->stream2));
-  }
   {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
     static const int seg_env = getenv("RAFT_B200_CONV7_SEG") ? atoi(getenv("RAFT_B200_CONV7_SEG")) : 0;  // tuning knob
     const int seg = seg_env ? seg_env : ((long)B * h * w <= 16384 ? 16 : 32);  // same-box A/B at 55x128: 792 / 772 / 781 us per 4 iterations for 32 / 16 / 8
@@ -709,11 +695,6 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     int zr = pass == 0 ? P_ZR1 : P_ZR2, q = pass == 0 ? P_Q1 : P_Q2;
     ConvParams p = base_params(v, L, blob, zr, W.hx, v.hx, 0, B, h, w);
     hoist_inp(v, W, pass * 2 + 0, p);
-    if (pass == 0 && zr1_side) {  // only the motion / flow channels are left for the main conv
-      p.ck_begin = (v.hidden + v.ctx) / 64; p.ck_count = v.hx / 64 - p.ck_begin; p.ck_skip_at = 1 << 20; p.ck_skip = 0;
-      p.addend = W.pre_h;
-      RB_CHECK_CUDA(cudaStreamWaitEvent(s, ss->join2, 0));
-    }
     static const int stash = getenv("RAFT_B200_NO_STASH") ? 0 : 1;  // A/B knob (common.cuh: Stash)
     p.epi = EPI_ZR; p.f0 = W.Z; p.f1 = W.H; p.stash = stash;
     p.d0_hi = W.qx.hi; p.d0_lo = W.qx.lo; p.d0_stride = v.hx; p.d0_choff = 0;
