@@ -86,8 +86,8 @@ enum Epilogue : int {
   EPI_DELTA = 3,  // c<2: coords1(f1)[c] += v ; optional copy to f2
   EPI_F32 = 4,    // f0[pix*cout+c] = scale*v
   EPI_FH2 = 5     // flow_head/conv1 with conv2 folded in (tensor-core back end only): y = relu(acc+bias) is NOT stored; each
-                  // epilogue thread forms the 18 per-pixel dot products <y[c..], W2[tap][c..][o]> of ITS channels ->
-                  // fh2_part[pix][part][tap*2+o]; fh2_gather_kernel (update.cu) sums parts and 3x3 neighbours
+                  // epilogue thread forms, per 16-channel group, the 18 dot products <y[c..c+16), W2[tap][c..][o]> ->
+                  // fh2_part[pix][c/16][tap*2+o]; fh2_gather_kernel (update.cu) sums parts and 3x3 neighbours
 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1 };
 
@@ -107,7 +107,7 @@ struct ConvParams {
   double* stat_part;  // EPI_F32 + tensor-core wide epilogue: per-(sample, strip, channel) sum / sum of squares of the
   int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
   const float* fh2_w;  // EPI_FH2: fp32 [cout][20] = flow_head/conv2 weights W2[tap][c][o] at [c][tap*2+o] (18 used), per OUTPUT channel c of this conv
-  float* fh2_part;     // EPI_FH2: [pixel][fh2_parts][18] partial dot products; part = cout-tile * column groups + column group
+  float* fh2_part;     // EPI_FH2: [pixel][fh2_parts][18] partial dot products; part = output channel / 16
   int fh2_parts;
   int stash;      // 1: single-tile CTAs park the gate epilogues' fp32 operands in spare TMEM columns during the MMA loop
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)

@@ -296,11 +296,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (dbg && warp == 2 && lane == 0) dbg[5] = gtime_ns();
         }
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ab * Cfg::kAccCols;
-        float acc2[18];
-        if constexpr (FH2) {
-#pragma unroll
-          for (int i = 0; i < 18; ++i) acc2[i] = 0.f;
-        }
 #pragma unroll 1
         for (int cc = 0; cc < Cfg::kColsPerWarp; cc += 16) {
           const int c = grp * Cfg::kColsPerWarp + cc;
@@ -315,9 +310,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if constexpr (FH2) {
             // y = relu(acc + bias) (model_utils.py:133), then this thread's share of conv2 (model_utils.py:134):
             // acc2[tap*2+o] += y[c] * W2[tap][c][o] in fp32; the weights row of a channel is one broadcast 80-byte read
-            float bsv[16];
+            // One partial per 16-CHANNEL GROUP (part = channel / 16), whatever the tile width: the summation partition must
+            // not depend on the launch geometry, or a batched run would differ from the per-sample runs in the last bit.
+            float bsv[16], acc2[18];
             ld256_nc(p.bias + n0 + c, bsv);
             ld256_nc(p.bias + n0 + c + 8, bsv + 8);
+#pragma unroll
+            for (int i = 0; i < 18; ++i) acc2[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float y = fmaxf(v[i] + bsv[i], 0.f);
@@ -329,6 +328,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               acc2[8] = fmaf(y, w2.x, acc2[8]); acc2[9] = fmaf(y, w2.y, acc2[9]); acc2[10] = fmaf(y, w2.z, acc2[10]); acc2[11] = fmaf(y, w2.w, acc2[11]);
               acc2[12] = fmaf(y, w3.x, acc2[12]); acc2[13] = fmaf(y, w3.y, acc2[13]); acc2[14] = fmaf(y, w3.z, acc2[14]); acc2[15] = fmaf(y, w3.w, acc2[15]);
               acc2[16] = fmaf(y, w4.x, acc2[16]); acc2[17] = fmaf(y, w4.y, acc2[17]);
+            }
+            if (valid) {
+              float2* dst = reinterpret_cast<float2*>(p.fh2_part + ((size_t)pix * p.fh2_parts + ((n0 + c) >> 4)) * 18);
+#pragma unroll
+              for (int i = 0; i < 9; ++i) dst[i] = make_float2(acc2[2 * i], acc2[2 * i + 1]);
             }
           }
           if (!FH2 && (valid || stash_row != 0)) {  // with a stash the TMEM reads inside are warp-collective: all lanes go
@@ -352,13 +356,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               dst[0] = (double)s1;
               dst[p.cout] = (double)s2;
             }
-          }
-        }
-        if constexpr (FH2) {
-          if (valid) {
-            float2* dst = reinterpret_cast<float2*>(p.fh2_part + ((size_t)pix * p.fh2_parts + nt * Cfg::kGroups + grp) * 18);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) dst[i] = make_float2(acc2[2 * i], acc2[2 * i + 1]);
           }
         }
         // this warp no longer needs the accumulator buffer: hand it back to the MMA warp
@@ -531,10 +528,9 @@ static int launch_fh2(const ConvParams& p, const TileGeom& g, const CUtensorMap*
     RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set.set(dev);
   }
-  RB_REQUIRE(p.fh2_w && p.fh2_part && p.fh2_parts == g.n_tiles * Cfg::kGroups && p.cout % 16 == 0 && p.bias && !p.addend &&
+  RB_REQUIRE(p.fh2_w && p.fh2_part && p.fh2_parts == p.cout / 16 && p.cout % 16 == 0 && p.bias && !p.addend &&
                  (reinterpret_cast<uintptr_t>(p.bias) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.fh2_w) & 15) == 0,
-             RB_ERR_BAD_ARG, "conv_tc: EPI_FH2 launch is inconsistent (parts %d, tiles %d x groups %d)", p.fh2_parts, g.n_tiles,
-             Cfg::kGroups);
+             RB_ERR_BAD_ARG, "conv_tc: EPI_FH2 launch is inconsistent (parts %d, cout %d)", p.fh2_parts, p.cout);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   int units = num_sms;
@@ -553,8 +549,7 @@ static int launch_fh2(const ConvParams& p, const TileGeom& g, const CUtensorMap*
   RB_CHECK_LAUNCH("conv_tc_kernel<FH2>");
   return RB_OK;
 }
-// parts of fh2_part the EPI_FH2 launch of a conv with `cout` channels produces (tile width as launch_conv_tc picks it)
-int conv_tc_fh2_parts(const ConvParams& p);
+int conv_tc_fh2_parts(const ConvParams& p);  // parts of fh2_part an EPI_FH2 launch produces
 
 template <int BLOCK_N, bool PAIR>
 static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
@@ -642,13 +637,7 @@ int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
 }
 #endif
 
-static int groups_of(int bn) { return bn >= 96 ? bn / 32 : bn / 16; }  // TcCfg<bn>::kGroups
-int conv_tc_fh2_parts(const ConvParams& p) {
-  const TileGeom g = choose_geom(p.h, p.w);
-  const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
-  const int bn = choose_block_n(p.cout, m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
-  return ((p.cout + bn - 1) / bn) * groups_of(bn);
-}
+int conv_tc_fh2_parts(const ConvParams& p) { return p.cout / 16; }  // one partial per 16-channel group (EPI_FH2)
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
 #ifdef RB_EXPERIMENTS
