@@ -528,6 +528,35 @@ __device__ __forceinline__ void warp_stats16(const float* y, float& s, float& s2
   ch = (int)(((lane >> 4) & 1u) * 8u + ((lane >> 3) & 1u) * 4u + ((lane >> 2) & 1u) * 2u + ((lane >> 1) & 1u));
 }
 
+// ---- flow_head/conv2 folded into conv1 (EPI_FH2): the 3x3 gather over the per-pixel partial products -------------------
+// G[q][s][tap*2+o] (s = 16-channel group of conv1's output) -> delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o],
+// zero outside the image (SAME padding of conv1's activations).  One WARP per pixel: item = tap * parts + s is spread over
+// the lanes (ascending per lane), then a fixed xor butterfly: the summation order is a function of `parts` only, so the
+// stand-alone kernel (update.cu) and the lookup kernel that applies the delta itself (corr.cu) give identical bits.
+struct Fh2Gather {
+  const float* part;  // nullptr: nothing to apply
+  const float* bias;  // [2]
+  int parts, h, w;
+};
+__device__ __forceinline__ float2 fh2_delta_warp(const Fh2Gather& g, int b, int y, int x, int lane) {
+  float d0 = 0.f, d1 = 0.f;
+  for (int it = lane; it < 9 * g.parts; it += 32) {
+    const int t = it / g.parts, s = it - t * g.parts;
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy >= 0 && yy < g.h && xx >= 0 && xx < g.w) {
+      const float2 v = *reinterpret_cast<const float2*>(g.part + ((size_t)((b * g.h + yy) * g.w + xx) * g.parts + s) * 18 + t * 2);
+      d0 += v.x;
+      d1 += v.y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+  }
+  return make_float2(d0 + g.bias[0], d1 + g.bias[1]);
+}
+
 // back ends
 int launch_conv_simt(const ConvParams& p, cudaStream_t s);
 int launch_conv_tc(const ConvParams& p, cudaStream_t s);

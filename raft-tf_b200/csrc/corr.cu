@@ -123,31 +123,39 @@ __device__ __forceinline__ int patch_idx(int row, int col, int phase) {
   return row * kPatchCols + ((((col >> 2) ^ ((row >> 1) + phase)) & 3) << 2) + (col & 3);
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 template <int R>
 struct LookupSmem {
   static constexpr int D = 2 * R + 1, K = D * D, UNITS = kLookupPB * 4;
   static constexpr int OUTP = (4 * K + 7) / 8 * 8;  // staged channels per pixel and plane (324 -> 328, 196 -> 200)
   static constexpr int kPatchOff = 0;
-  static constexpr int kXtabOff = UNITS * kUnitBytes;              // float2 [UNITS][D]: (qx, packed ax0 | ax1 << 8)
-  static constexpr int kOutOff = kXtabOff + UNITS * D * 8;         // half [PB][2][OUTP]
-  static constexpr int kBaseOff = kOutOff + kLookupPB * 2 * OUTP * 2;  // int [UNITS][2]: bx4, by
+  static constexpr int kXtabOff = UNITS * kUnitBytes;              // float2 [UNITS][D]: (qx, 4*col of x0 | 4*col of x1 << 8)
+  static constexpr int kOutOff = kXtabOff + UNITS * D * 8;         // float [PB][OUTP]: results before the hi/lo split
+  static_assert(3 * (kOutOff + kLookupPB * OUTP * 4 + UNITS * 8 + 16 + kLookupPB * 8 + 1024) <= 228 * 1024, "three blocks per SM");
+  static constexpr int kBaseOff = kOutOff + kLookupPB * OUTP * 4;  // int [UNITS][2]: bx4, by
   static constexpr int kBarOff = kBaseOff + UNITS * 8;
-  static constexpr int kBytes = kBarOff + 16;
+  static constexpr int kBytes = kBarOff + 16 + kLookupPB * 8;  // + float2 [PB]: the block's coordinates
 };
 
 template <int R, bool SPLIT>
-__global__ void __launch_bounds__(kLookupPB * 4 * (2 * R + 1))
+__global__ void __launch_bounds__(kLookupPB * 4 * (2 * R + 1), 3)
 corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMaps maps,
-                   const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
-                   __half* __restrict__ out_lo, int out_stride, int npix) {
+                   float2* coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
+                   __half* __restrict__ out_lo, int out_stride, int npix, const Fh2Gather gat) {
   using L = LookupSmem<R>;
   constexpr int D = L::D, K = L::K, P = D + 2, UNITS = L::UNITS, NT = UNITS * D, OUTP = L::OUTP;
   extern __shared__ __align__(1024) uint8_t lk_smem[];  // no static shared memory in this kernel: the slots start at 0
   float* patch = reinterpret_cast<float*>(lk_smem + L::kPatchOff);
   float2* xtab = reinterpret_cast<float2*>(lk_smem + L::kXtabOff);
-  __half* ostage = reinterpret_cast<__half*>(lk_smem + L::kOutOff);
+  float* ostage = reinterpret_cast<float*>(lk_smem + L::kOutOff);
   int* ubase = reinterpret_cast<int*>(lk_smem + L::kBaseOff);
   uint64_t* bar = reinterpret_cast<uint64_t*>(lk_smem + L::kBarOff);
+  float2* cnew = reinterpret_cast<float2*>(lk_smem + L::kBarOff + 16);  // [PB] coordinates of the block's pixels
   const int tid = threadIdx.x;
   const int pix0 = blockIdx.x * kLookupPB;
 
@@ -162,9 +170,9 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
     if (n_tma) tc::mbar_arrive_expect_tx(bar, (uint32_t)(n_tma * P * kPatchCols * 4));
   }
   if (SPLIT) {  // channel padding of the staged output rows (never produced by a tap)
-    for (int e = tid; e < kLookupPB * 2 * (OUTP - 4 * K); e += NT) {
+    for (int e = tid; e < kLookupPB * (OUTP - 4 * K); e += NT) {
       const int row = e / (OUTP - 4 * K), c = 4 * K + e % (OUTP - 4 * K);
-      ostage[row * OUTP + c] = __float2half_rn(0.f);
+      ostage[row * OUTP + c] = 0.f;
     }
   }
   __syncthreads();
@@ -172,6 +180,20 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   // nothing above touched global memory, everything below comes after the predecessor kernel.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ---- coordinates of the block's pixels; inside the iteration loop the previous step's flow update is applied HERE
+  // (coords1 += delta_flow, RAFT.py:102: the delta is the 3x3 gather over conv1's partial products, fh2_delta_warp) instead
+  // of by a kernel of its own between the flow head and this lookup --------------------------------------------------------
+  for (int pl = tid >> 5; pl < kLookupPB; pl += NT / 32) {
+    const int pix = min(pix0 + pl, npix - 1);
+    float2 c = coords[pix];
+    if (gat.part) {
+      const float2 d = fh2_delta_warp(gat, pix / (gat.w * gat.h), (pix / gat.w) % gat.h, pix % gat.w, tid & 31);
+      c.x += d.x; c.y += d.y;
+      if ((tid & 31) == 0 && pix0 + pl < npix) coords[pix] = c;
+    }
+    if ((tid & 31) == 0) cnew[pl] = c;
+  }
+  __syncthreads();
   // ---- phase 0: per-unit origin, TMA issue --------------------------------------------------------------
   // The 64 units are spread over the first lanes of ALL warps: every lane issues its own TMA with its own operands,
   // which ptxas serialises per warp (one elect / R2UR round per distinct lane) -- 4-5 rounds per warp instead of 32 in 2.
@@ -179,7 +201,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   if ((tid & 31) < kUnitsPerWarp && (tid >> 5) * kUnitsPerWarp + (tid & 31) < UNITS) {
     const int u = (tid >> 5) * kUnitsPerWarp + (tid & 31), pl = u >> 2, lvl = u & 3;
     const int pix = min(pix0 + pl, npix - 1);
-    const float2 c = __ldg(coords + pix);
+    const float2 c = cnew[pl];
     const float inv = 1.0f / (float)(1 << lvl);  // centroid / 2**i (model_utils.py:239), exact
     const int H = pv.hl[lvl], W = pv.wl[lvl];
     const float xf0 = __fadd_rn(c.x * inv, (float)(-R)), yf0 = __fadd_rn(c.y * inv, (float)(-R));
@@ -211,7 +233,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   const int pl = u >> 2, lvl = u & 3;
   const int pix = pix0 + pl;
   const int H = pv.hl[lvl], W = pv.wl[lvl];
-  const float2 c = __ldg(coords + min(pix, npix - 1));
+  const float2 c = cnew[pl];
   const float inv = 1.0f / (float)(1 << lvl);
   const float cx = c.x * inv, cy = c.y * inv;
   {
@@ -224,7 +246,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
     const float qx = __fsub_rn((float)x1, x);  // utils.py:84 (clamped x1)
     const int bx4 = ubase[2 * u];
     const int ax0 = min(max(x0 - bx4, 0), kPatchCols - 1), ax1 = min(max(x1 - bx4, 0), kPatchCols - 1);
-    xtab[u * D + j] = make_float2(qx, __int_as_float(ax0 | (ax1 << 8)));
+    xtab[u * D + j] = make_float2(qx, __int_as_float((ax0 * 4) | (ax1 * 4 << 8)));
   }
   const float y = __fadd_rn(cy, (float)(j - R));
   int y0 = (int)y;
@@ -234,9 +256,14 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   const float qy = __fsub_rn((float)y1, y), pyw = __fsub_rn(1.0f, qy);  // utils.py:85
   const int by = ubase[2 * u + 1];
   const int r0 = min(max(y0 - by, 0), P - 1), r1 = min(max(y1 - by, 0), P - 1);
-  const float* pu = patch + u * (kUnitBytes / 4);
+  // Texel address = (swizzled row address) XOR (4 * column): rows are 64 bytes and CU_TENSOR_MAP_SWIZZLE_64B XORs the 16-byte
+  // chunk index with ((slot_base / 128 + row / 2) & 3), i.e. only bits 4-5 of the offset inside the row -- so the row part
+  // (64-byte aligned address + chunk phase << 4) and the column part (4 * col < 64) combine with ONE xor per texel.
+  // (r01 version: ~16 integer instructions of swizzle arithmetic per tap, 75 SASS instructions per tap in total; now 21.)
   const int phase = (u * (kUnitBytes / 128)) & 3;
-  const int r0b = r0 * kPatchCols, r0x = ((r0 >> 1) + phase) & 3, r1b = r1 * kPatchCols, r1x = ((r1 >> 1) + phase) & 3;
+  const uint32_t ubase_a = tc::smem_u32(lk_smem) + u * kUnitBytes;
+  const uint32_t r0a = ubase_a + r0 * 64 + ((((r0 >> 1) + phase) & 3) << 4);
+  const uint32_t r1a = ubase_a + r1 * 64 + ((((r1 >> 1) + phase) & 3) << 4);
   __syncthreads();                     // xtab + fallback patches visible
   if (n_tma) tc::mbar_wait(bar, 0);    // TMA patches landed
   // ---- phase 2: taps of window row j ------------------------------------------------------------------------------
@@ -244,41 +271,41 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     const float2 xt = xtab[u * D + i];
-    const int packed = __float_as_int(xt.y), ax0 = packed & 0xff, ax1 = packed >> 8;
-    const int c0h = ax0 >> 2, c0l = ax0 & 3, c1h = ax1 >> 2, c1l = ax1 & 3;
+    const uint32_t pk = (uint32_t)__float_as_int(xt.y), c0 = pk & 0xffu, c1 = pk >> 8;
     const float pxw = __fsub_rn(1.0f, xt.x);
     const float wa = __fmul_rn(xt.x, qy), wb = __fmul_rn(xt.x, pyw);  // utils.py:86-89
     const float wc = __fmul_rn(pxw, qy), wd = __fmul_rn(pxw, pyw);
-    const float Ia = pu[r0b + (((c0h ^ r0x) & 3) << 2) + c0l], Ib = pu[r1b + (((c0h ^ r1x) & 3) << 2) + c0l];
-    const float Ic = pu[r0b + (((c1h ^ r0x) & 3) << 2) + c1l], Id = pu[r1b + (((c1h ^ r1x) & 3) << 2) + c1l];
+    const float Ia = lds_f32(r0a ^ c0), Ib = lds_f32(r1a ^ c0), Ic = lds_f32(r0a ^ c1), Id = lds_f32(r1a ^ c1);
     const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
                               __fmul_rn(wd, Id));  // tf.add_n order (utils.py:98)
     const int ch = lvl * K + i * D + j;
     if constexpr (SPLIT) {
-      __half hi, lo;
-      split_f32(v, hi, lo);
-      ostage[(pl * 2 + 0) * OUTP + ch] = hi;
-      ostage[(pl * 2 + 1) * OUTP + ch] = lo;
+      ostage[pl * OUTP + ch] = v;
     } else {
       if (live) out_f32[(size_t)pix * out_stride + ch] = v;
     }
   }
-  // ---- phase 3: coalesced 16-byte stores of the staged rows ----------------------------------------------------------
+  // ---- phase 3: hi/lo split of 8 consecutive channels per thread, 16-byte stores per plane ---------------------------------
   if constexpr (SPLIT) {
     __syncthreads();
-    constexpr int V = OUTP / 8;  // uint4 per pixel-plane
-    for (int e = tid; e < kLookupPB * 2 * V; e += NT) {
-      const int row = e / V, v8 = e - row * V, p2 = row >> 1, plane = row & 1;
+    constexpr int V = OUTP / 8;  // 8-channel groups per pixel
+    for (int e = tid; e < kLookupPB * V; e += NT) {
+      const int p2 = e / V, v8 = e - p2 * V;
       if (pix0 + p2 >= npix) continue;
-      const uint4 val = *reinterpret_cast<const uint4*>(ostage + row * OUTP + v8 * 8);
-      __half* dst = (plane ? out_lo : out_hi) + (size_t)(pix0 + p2) * out_stride + v8 * 8;
-      *reinterpret_cast<uint4*>(dst) = val;
+      const float4 a = *reinterpret_cast<const float4*>(ostage + p2 * OUTP + v8 * 8);
+      const float4 b = *reinterpret_cast<const float4*>(ostage + p2 * OUTP + v8 * 8 + 4);
+      uint4 h, l;
+      split2(a.x, a.y, h.x, l.x); split2(a.z, a.w, h.y, l.y);
+      split2(b.x, b.y, h.z, l.z); split2(b.z, b.w, h.w, l.w);
+      *reinterpret_cast<uint4*>(out_hi + (size_t)(pix0 + p2) * out_stride + v8 * 8) = h;
+      *reinterpret_cast<uint4*>(out_lo + (size_t)(pix0 + p2) * out_stride + v8 * 8) = l;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// A2/A3 lookup, v5 (round 2; default).  What the r01 profile said about v4: 75 SASS instructions per tap (swizzle /
+// A2/A3 lookup, warp-per-pixel form ("v5", round 2): the kernel of the VOLUME-FREE path (OTF = true) and an opt-in
+// alternative for the materialised volume (RAFT_B200_LOOKUP_V5=1).  What the r01 profile said about the round-1 kernel: 75 SASS instructions per tap (swizzle /
 // index arithmetic), 1.86x more DRAM bytes than the algorithmic count (16-column, (2r+3)-row boxes promoted to 256-byte
 // L2 requests).  v5:
 //   * one WARP per query pixel, its 4 pyramid levels = 4 units; lane = tap (t = i*D + j, ceil(K/32) rounds), so the
@@ -325,12 +352,6 @@ struct PyramidMapsV5 {
 // start of shared memory: rows are 64 bytes; CU_TENSOR_MAP_SWIZZLE_64B XORs the 16-byte chunk index with bits [7,9) of the
 // shared-memory byte address, i.e. with s(row) = (unit_off / 128 + row / 2) & 3.
 __device__ __forceinline__ int v5_row_off(int unit_off, int row) { return row * 64 + ((((unit_off >> 7) + (row >> 1)) & 3) << 4); }
-
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
 
 template <int R, bool SPLIT, bool OTF = false>
 __global__ void __launch_bounds__(LookupV5<R, OTF>::NT, OTF ? 2 : 3)
@@ -612,8 +633,8 @@ static size_t lookup_smem_bytes() {
 }
 
 template <int R, bool SPLIT>
-static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, const float2* c2, float* out_f32, __half* out_hi,
-                             __half* out_lo, int out_stride, int npix, cudaStream_t s) {
+static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, float2* c2, float* out_f32, __half* out_hi,
+                             __half* out_lo, int out_stride, int npix, cudaStream_t s, const Fh2Gather& gat) {
   static PerDeviceOnce attr_set;
   const size_t smem = lookup_smem_bytes<R>();
   int dev = 0, rc_dev;
@@ -638,7 +659,7 @@ static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix));
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix, gat));
   RB_CHECK_LAUNCH("corr_lookup_kernel");
   return RB_OK;
 }
@@ -671,8 +692,9 @@ static int launch_lookup_v5(const PyramidView& pv, const PyramidMapsV5& maps, co
   return RB_OK;
 }
 
+// apply_delta != nullptr: coords is READ-WRITE -- the kernel first adds the pending flow update to it (Fh2Gather, common.cuh)
 int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
-                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s) {
+                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s, const Fh2Gather* apply_delta) {
   PyramidView pv;
   int rc = pyramid_view(pyramid, B, h, w, &pv);
   if (rc) return rc;
@@ -681,10 +703,17 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
              out_stride);
   const int npix = B * h * w;
   const float2* c2 = reinterpret_cast<const float2*>(coords);
+  float2* c2rw = const_cast<float2*>(c2);  // written only when apply_delta is set (the caller passed a mutable buffer)
+  Fh2Gather gat{nullptr, nullptr, 0, h, w};
+  if (apply_delta) gat = *apply_delta;
   const bool split = out_hi != nullptr;
-  static const bool v4 = getenv("RAFT_B200_LOOKUP_V4") != nullptr;  // A/B: the round-1 kernel (16-column swizzled boxes)
+  // Default: corr_lookup_kernel (block = 16 px x 4 levels, thread = window row).  RAFT_B200_LOOKUP_V5=1 selects the
+  // warp-per-pixel kernel (lane = tap) that the volume-free path is built on: same DRAM traffic, 29 % shared-memory bank
+  // conflicts (nine window rows of one column can never sit in nine distinct bank groups) -- 14 % slower at batch 8
+  // (profiles/r02_notes.md), kept selectable because it shares every line with the volume-free instantiation.
+  static const bool v5 = getenv("RAFT_B200_LOOKUP_V5") != nullptr;
   const bool f32_rows_ok = split || (out_stride % 4 == 0 && reinterpret_cast<uintptr_t>(out_f32) % 16 == 0);
-  if (!v4 && f32_rows_ok) {
+  if (v5 && f32_rows_ok && !apply_delta) {
     PyramidMapsV5 maps;
     memset(&maps, 0, sizeof(maps));
     for (int l = 0; l < RB_NUM_LEVELS; ++l) {
@@ -713,10 +742,10 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
     if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_SW64) != RB_OK) pv.tma_ok[l] = 0;  // plain loads instead
   }
   if (radius == 4)
-    return split ? launch_lookup_cfg<4, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
-                 : launch_lookup_cfg<4, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
-  return split ? launch_lookup_cfg<3, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
-               : launch_lookup_cfg<3, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
+    return split ? launch_lookup_cfg<4, true>(pv, maps, c2rw, nullptr, out_hi, out_lo, out_stride, npix, s, gat)
+                 : launch_lookup_cfg<4, false>(pv, maps, c2rw, out_f32, nullptr, nullptr, out_stride, npix, s, gat);
+  return split ? launch_lookup_cfg<3, true>(pv, maps, c2rw, nullptr, out_hi, out_lo, out_stride, npix, s, gat)
+               : launch_lookup_cfg<3, false>(pv, maps, c2rw, out_f32, nullptr, nullptr, out_stride, npix, s, gat);
 }
 
 // ---- F2: volume-free correlation ---------------------------------------------------------------------------------------------
@@ -846,7 +875,7 @@ extern "C" int rb_corr_lookup(const float* pyramid, const float* coords, float* 
   RB_REQUIRE(pyramid && coords && out, RB_ERR_BAD_ARG, "rb_corr_lookup: null pointer");
   RB_REQUIRE(B > 0 && h > 0 && w > 0, RB_ERR_BAD_SHAPE, "rb_corr_lookup: bad shape");
   int K = (2 * radius + 1) * (2 * radius + 1);
-  return launch_lookup(pyramid, coords, out, nullptr, nullptr, 4 * K, B, h, w, radius, (cudaStream_t)stream);
+  return launch_lookup(pyramid, coords, out, nullptr, nullptr, 4 * K, B, h, w, radius, (cudaStream_t)stream, nullptr);
 }
 
 /* ---- F2: volume-free correlation; same results as rb_corr_build + rb_corr_lookup up to fp32 summation order ---- */

@@ -22,7 +22,8 @@
 namespace rb {
 
 int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
-                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s);
+                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s,
+                  const Fh2Gather* apply_delta = nullptr);
 int launch_lookup_otf(const float* fmap1, const float* fmap2, const float* pooled, const float* coords, float* out_f32,
                       __half* out_hi, __half* out_lo, int out_stride, int B, int h, int w, int C, int radius, cudaStream_t s);
 
@@ -459,43 +460,25 @@ static int launch_flow_head2(const ConvParams& p, cudaStream_t s) {
 // G[q][s][tap*2+o] = sum over the part's channels of relu(conv1)[q][c] * W2[tap][c][o].  The 3x3 conv (SAME: zero outside
 // the image) is then  delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o]  -- fixed summation order
 // (tap-major, parts ascending): bit-reproducible, batched == per-sample.  coords1 += delta (RAFT.py:102).
-// One WARP per pixel: the 9 * parts partial pairs are spread over the lanes (item = tap * parts + part), each lane sums its
-// items in ascending order and a fixed xor butterfly finishes the sum.  (First version: one thread per pixel walking 72
-// dependent-latency loads -- 11 us per launch in the r02 ncu list for 4 MB of L2-resident data.)
-__global__ void __launch_bounds__(256) fh2_gather_kernel(const float* __restrict__ part, int parts, const float* __restrict__ bias,
-                                                         float* coords1, float* delta_out, int B, int h, int w) {
+// Stand-alone form (rb_update_step, and the last iteration of rb_raft_iterate): one warp per pixel, fh2_delta_warp of
+// common.cuh.  Inside the loop the NEXT iteration's lookup kernel applies the delta itself (corr.cu), which removes this
+// launch and one kernel boundary from the dependent chain of every iteration.
+__global__ void __launch_bounds__(256) fh2_gather_kernel(const Fh2Gather g, float* coords1, float* delta_out, int B) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= B * h * w) return;  // warp-uniform
-  const int x = i % w, y = (i / w) % h, b = i / (w * h);
-  float d0 = 0.f, d1 = 0.f;
-  for (int it = lane; it < 9 * parts; it += 32) {
-    const int t = it / parts, s = it - t * parts;
-    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {  // SAME padding: conv1's activations are zero outside the image
-      const float2 v = __ldg(reinterpret_cast<const float2*>(part + ((size_t)((b * h + yy) * w + xx) * parts + s) * 18 + t * 2));
-      d0 += v.x;
-      d1 += v.y;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-  }
+  if (i >= B * g.h * g.w) return;  // warp-uniform
+  const float2 d = fh2_delta_warp(g, i / (g.w * g.h), (i / g.w) % g.h, i % g.w, lane);
   if (lane == 0) {
-    d0 += bias[0];
-    d1 += bias[1];
     float2 c = *reinterpret_cast<float2*>(coords1 + (size_t)i * 2);
-    c.x += d0; c.y += d1;
+    c.x += d.x; c.y += d.y;  // RAFT.py:102
     *reinterpret_cast<float2*>(coords1 + (size_t)i * 2) = c;
-    if (delta_out) *reinterpret_cast<float2*>(delta_out + (size_t)i * 2) = make_float2(d0, d1);
+    if (delta_out) *reinterpret_cast<float2*>(delta_out + (size_t)i * 2) = d;
   }
 }
 
-static int launch_fh2_gather(const float* part, int parts, const float* bias, float* coords1, float* delta_out, int B, int h,
-                             int w, cudaStream_t s) {
+static int launch_fh2_gather(const Fh2Gather& g, float* coords1, float* delta_out, int B, cudaStream_t s) {
+  const int h = g.h, w = g.w;
   static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -507,7 +490,7 @@ static int launch_fh2_gather(const float* part, int parts, const float* bias, fl
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fh2_gather_kernel, part, parts, bias, coords1, delta_out, B, h, w));
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fh2_gather_kernel, g, coords1, delta_out, B));
   RB_CHECK_LAUNCH("fh2_gather_kernel");
   return RB_OK;
 }
@@ -580,9 +563,13 @@ static int side_stream(SideStream** out) {
   return RB_OK;
 }
 
-// pyramid != nullptr: the lookup for this iteration is issued here too (on the main branch)
+// pyramid != nullptr: the lookup for this iteration is issued here too (on the main branch).
+// delta_in: coords1 still lacks the previous step's delta -- this step's lookup kernel applies it (needs pyramid);
+// defer_delta: leave THIS step's delta in W.fh2_part for the next step's lookup (only honoured when the conv2 fold is on;
+// *deferred reports what happened).
 static int update_step(const Variant& v, const void* blob, void* wsp, float* coords1, float* delta_out,
-                       float* mask_out, int B, int h, int w, cudaStream_t s, const float* pyramid = nullptr) {
+                       float* mask_out, int B, int h, int w, cudaStream_t s, const float* pyramid = nullptr,
+                       bool delta_in = false, bool defer_delta = false, bool* deferred = nullptr) {
   const size_t npix = (size_t)B * h * w;
   const PackedLayout L = packed_layout(v);
   const Workspace W = workspace_layout(v, npix, wsp);
@@ -607,6 +594,13 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   // ---- motion encoder (model_utils.py:110-129) ----
   SideStream* ss;
   if ((rc = side_stream(&ss))) return rc;
+  if (deferred) *deferred = false;
+  const float* fh2_bias = reinterpret_cast<const float*>(bb + L.bias[P_FH2]);
+  if (delta_in) {  // the lookup applies the pending delta and rewrites coords1: the flow branch may only fork after it
+    RB_REQUIRE(pyramid, RB_ERR_BAD_ARG, "internal: a pending delta needs the lookup of this step");
+    Fh2Gather g{W.fh2_part, fh2_bias, L.cout[P_FH1] / 16, h, w};
+    if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s, &g))) return rc;
+  }
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
   {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
@@ -636,7 +630,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     RB_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
   }
   // correlation branch (main stream): [lookup ->] convc1 [-> convc2]
-  if (pyramid) {
+  if (pyramid && !delta_in) {
     if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s))) return rc;
   }
 #ifdef RB_EXPERIMENTS
@@ -724,8 +718,12 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     }
     if ((rc = launch_conv_dbg(p, s))) return rc;
     if (fuse) {
-      const float* b2 = reinterpret_cast<const float*>(bb + L.bias[P_FH2]);
-      if ((rc = launch_fh2_gather(W.fh2_part, p.fh2_parts, b2, coords1, delta_out, B, h, w, s))) return rc;
+      if (defer_delta && !delta_out) {
+        if (deferred) *deferred = true;  // the next step's lookup kernel adds it to coords1
+      } else {
+        Fh2Gather g{W.fh2_part, fh2_bias, p.fh2_parts, h, w};
+        if ((rc = launch_fh2_gather(g, coords1, delta_out, B, s))) return rc;
+      }
     } else {
       p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
       p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
@@ -977,9 +975,16 @@ extern "C" int rb_raft_iterate(int small, const void* weights, void* workspace, 
   int rc = check_shape("rb_raft_iterate", B, h, w);
   if (rc) return rc;
   const Variant& v = variant(small);
+  // RAFT_B200_NO_DELTA_FUSE=1: every step launches its own gather kernel (A/B knob)
+  static const bool no_defer = getenv("RAFT_B200_NO_DELTA_FUSE") != nullptr;
+  bool pending = false;
   for (int it = 0; it < iters; ++it) {
     float* m = (it == iters - 1 && !small) ? mask_out : nullptr;
-    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream, pyramid))) return rc;
+    bool deferred = false;
+    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream, pyramid, pending,
+                          !no_defer && it + 1 < iters, &deferred)))
+      return rc;
+    pending = deferred;
   }
   return RB_OK;
 }

@@ -30,11 +30,12 @@ def test_variant_passes_conv_and_update_parity(cuda, knob):
     _kernel_parity(dict(os.environ, **{knob: "1"}))
 
 
-def test_round1_lookup_kernel_still_bit_exact(cuda):
-    """RAFT_B200_LOOKUP_V4=1 selects the round-1 lookup kernel (16-column swizzled boxes), kept as the A/B partner of v5."""
+def test_warp_per_pixel_lookup_kernel_bit_exact(cuda):
+    """RAFT_B200_LOOKUP_V5=1 selects the warp-per-pixel lookup kernel (the one the volume-free path instantiates) for the
+    materialised volume: same bit-exact results."""
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_kernels.py"), "-q", "-x",
                         "-k", "lookup", "--timeout", "300", "-p", "no:cacheprovider"],
-                       env=dict(os.environ, RAFT_B200_LOOKUP_V4="1"), cwd=ROOT, capture_output=True, text=True, timeout=900)
+                       env=dict(os.environ, RAFT_B200_LOOKUP_V5="1"), cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 

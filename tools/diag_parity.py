@@ -44,4 +44,11 @@ if a.simt:
     m.engine().math_mode = capi.RB_MATH_SIMT
 out = m.forward(l, r).cpu()
 e32, e64 = (out - r32).abs(), (out.double() - r64).abs()
+bad = (e64.max(-1).values[0] > 1e-3).nonzero()
+if len(bad):
+    ys, xs = bad[:, 0], bad[:, 1]
+    print(f"   {len(bad)} pixels above 1e-3 ({100.0 * len(bad) / (a.H * a.W):.4f} %): rows {int(ys.min())}..{int(ys.max())}, cols {int(xs.min())}..{int(xs.max())}; "
+          f"coarse cells {sorted(set((int(y) // 8, int(x) // 8) for y, x in bad.tolist()))[:12]}")
+    q = torch.quantile(e64.max(-1).values.flatten()[::7].float(), torch.tensor([0.5, 0.99, 0.9999]))
+    print(f"   error quantiles (50 / 99 / 99.99 %): {q[0]:.2e} / {q[1]:.2e} / {q[2]:.2e}")
 print(f"{a.tag or 'default':>24}: vs fp32 oracle {e32.max():.3e} (mean {e32.mean():.2e})   vs fp64 oracle {e64.max():.3e} (mean {e64.mean():.2e})")

@@ -20,16 +20,13 @@ fi
 echo "== lookup A/B"
 for B in 1 8; do
   for fl in "" "--flush"; do
-    echo -n "v5 promo=none B=$B $fl: "; timeout 200 python tools/micro.py lookup --B $B $fl 2>&1 | tail -1
-    echo -n "v4            B=$B $fl: "; RAFT_B200_LOOKUP_V4=1 timeout 200 python tools/micro.py lookup --B $B $fl 2>&1 | tail -1
-  done
-  for pr in 64 256; do
-    echo -n "v5 promo=$pr B=$B --flush: "; RAFT_B200_LOOKUP_L2PROMO=$pr timeout 200 python tools/micro.py lookup --B $B --flush 2>&1 | tail -1
+    echo -n "default       B=$B $fl: "; timeout 200 python tools/micro.py lookup --B $B $fl 2>&1 | tail -1
+    echo -n "v5 (opt-in)   B=$B $fl: "; RAFT_B200_LOOKUP_V5=1 timeout 200 python tools/micro.py lookup --B $B $fl 2>&1 | tail -1
   done
 done 2>&1 | tee $O/lookup_ab.log
 echo "== stage timings"
 for w in corr encoder update iterate forward; do timeout 200 python tools/micro.py $w 2>&1 | tail -1; done | tee $O/stages.log
-for knob in RAFT_B200_NO_FH2_FUSE RAFT_B200_NO_STASH RAFT_B200_LOOKUP_V4; do
+for knob in RAFT_B200_NO_FH2_FUSE RAFT_B200_NO_STASH RAFT_B200_NO_DELTA_FUSE RAFT_B200_LOOKUP_V5; do
   for w in update iterate; do echo -n "$knob=1 $w: "; env $knob=1 timeout 200 python tools/micro.py $w 2>&1 | tail -1; done
 done | tee -a $O/stages.log
 echo -n "B=8 update: "; timeout 200 python tools/micro.py update --B 8 2>&1 | tail -1 | tee -a $O/stages.log
@@ -44,6 +41,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:corr
     python tools/micro.py lookup --reps 3 --n 1 > $O/ncu_lookup1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:corr_lookup -s 2 -c 1 -f -o $O/r02_lookup_b8 \
     python tools/micro.py lookup --B 8 --reps 3 --n 1 > $O/ncu_lookup8.log 2>&1
+echo "== ncu full: corr build"
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|corr_prep" -s 5 -c 5 -f -o $O/r02_corr \
+    python tools/micro.py corr --reps 1 --n 1 > $O/ncu_corr.log 2>&1
 echo "== ncu full: update-step convs"
 RAFT_B200_NO_PDL=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:conv_tc|flow_conv7|fh2_gather" -s 15 -c 11 -f -o $O/r02_update \
     python tools/micro.py update --reps 2 --n 1 > $O/ncu_update.log 2>&1
