@@ -115,7 +115,7 @@ struct PyramidMaps {
 
 constexpr int kLookupPB = 16;    // pixels per block: 440 blocks of 576 threads at 440x1024 = ONE wave at 3 blocks/SM
 constexpr int kPatchCols = 16;   // staged columns per row (64 bytes)
-constexpr int kUnitBytes = 768;  // shared bytes per unit (>= (2r+3)*64); a multiple of 128 so the swizzle phase is known
+constexpr int kUnitBytes = 640;  // shared bytes per unit (>= (2r+2)*64); a multiple of 128 so the swizzle phase is known
 
 // float index of element (row, col) inside a unit's staged patch.  CU_TENSOR_MAP_SWIZZLE_64B XORs the 16-byte chunk
 // index with bits [7,9) of the shared-memory byte address = (slot_base/128 + row/2) & 3; `phase` = (slot_base/128) & 3.
@@ -145,10 +145,13 @@ struct LookupSmem {
 template <int R, bool SPLIT>
 __global__ void __launch_bounds__(kLookupPB * 4 * (2 * R + 1), 3)
 corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant__ PyramidMaps maps,
-                   float2* coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
-                   __half* __restrict__ out_lo, int out_stride, int npix, const Fh2Gather gat) {
+                   const float2* __restrict__ coords, float* __restrict__ out_f32, __half* __restrict__ out_hi,
+                   __half* __restrict__ out_lo, int out_stride, int npix) {
   using L = LookupSmem<R>;
-  constexpr int D = L::D, K = L::K, P = D + 2, UNITS = L::UNITS, NT = UNITS * D, OUTP = L::OUTP;
+  // P = rows staged per unit: the (2r+2)-row footprint.  The row the fp32 rounding of cy + dy can add (r01 staged it for
+  // every unit: +9 % DRAM bytes in a kernel that runs at 80 % of the HBM copy peak at batch 8) is handled by the threads
+  // that actually need it with four global loads per tap (`far`, below) -- about one window row in a million.
+  constexpr int D = L::D, K = L::K, P = D + 1, UNITS = L::UNITS, NT = UNITS * D, OUTP = L::OUTP;
   extern __shared__ __align__(1024) uint8_t lk_smem[];  // no static shared memory in this kernel: the slots start at 0
   float* patch = reinterpret_cast<float*>(lk_smem + L::kPatchOff);
   float2* xtab = reinterpret_cast<float2*>(lk_smem + L::kXtabOff);
@@ -180,19 +183,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   // nothing above touched global memory, everything below comes after the predecessor kernel.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // ---- coordinates of the block's pixels; inside the iteration loop the previous step's flow update is applied HERE
-  // (coords1 += delta_flow, RAFT.py:102: the delta is the 3x3 gather over conv1's partial products, fh2_delta_warp) instead
-  // of by a kernel of its own between the flow head and this lookup --------------------------------------------------------
-  for (int pl = tid >> 5; pl < kLookupPB; pl += NT / 32) {
-    const int pix = min(pix0 + pl, npix - 1);
-    float2 c = coords[pix];
-    if (gat.part) {
-      const float2 d = fh2_delta_warp(gat, pix / (gat.w * gat.h), (pix / gat.w) % gat.h, pix % gat.w, tid & 31);
-      c.x += d.x; c.y += d.y;
-      if ((tid & 31) == 0 && pix0 + pl < npix) coords[pix] = c;
-    }
-    if ((tid & 31) == 0) cnew[pl] = c;
-  }
+  if (tid < kLookupPB) cnew[tid] = __ldg(coords + min(pix0 + tid, npix - 1));  // the block's coordinates, read once
   __syncthreads();
   // ---- phase 0: per-unit origin, TMA issue --------------------------------------------------------------
   // The 64 units are spread over the first lanes of ALL warps: every lane issues its own TMA with its own operands,
@@ -255,6 +246,7 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
   y1 = min(max(y1, 0), H - 1);
   const float qy = __fsub_rn((float)y1, y), pyw = __fsub_rn(1.0f, qy);  // utils.py:85
   const int by = ubase[2 * u + 1];
+  const bool far = (y1 - by) > P - 1 || (y0 - by) > P - 1;  // rounding slack row outside the staged box
   const int r0 = min(max(y0 - by, 0), P - 1), r1 = min(max(y1 - by, 0), P - 1);
   // Texel address = (swizzled row address) XOR (4 * column): rows are 64 bytes and CU_TENSOR_MAP_SWIZZLE_64B XORs the 16-byte
   // chunk index with ((slot_base / 128 + row / 2) & 3), i.e. only bits 4-5 of the offset inside the row -- so the row part
@@ -275,7 +267,15 @@ corr_lookup_kernel(const __grid_constant__ PyramidView pv, const __grid_constant
     const float pxw = __fsub_rn(1.0f, xt.x);
     const float wa = __fmul_rn(xt.x, qy), wb = __fmul_rn(xt.x, pyw);  // utils.py:86-89
     const float wc = __fmul_rn(pxw, qy), wd = __fmul_rn(pxw, pyw);
-    const float Ia = lds_f32(r0a ^ c0), Ib = lds_f32(r1a ^ c0), Ic = lds_f32(r0a ^ c1), Id = lds_f32(r1a ^ c1);
+    float Ia, Ib, Ic, Id;
+    if (!far) {
+      Ia = lds_f32(r0a ^ c0); Ib = lds_f32(r1a ^ c0); Ic = lds_f32(r0a ^ c1); Id = lds_f32(r1a ^ c1);
+    } else {
+      const float* img = pv.base[lvl] + (size_t)min(pix, npix - 1) * H * W;
+      const int bx4 = ubase[2 * u], xa = bx4 + (int)(c0 >> 2), xb = bx4 + (int)(c1 >> 2);
+      Ia = __ldg(img + (size_t)y0 * W + xa); Ib = __ldg(img + (size_t)y1 * W + xa);
+      Ic = __ldg(img + (size_t)y0 * W + xb); Id = __ldg(img + (size_t)y1 * W + xb);
+    }
     const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)),
                               __fmul_rn(wd, Id));  // tf.add_n order (utils.py:98)
     const int ch = lvl * K + i * D + j;
@@ -633,8 +633,8 @@ static size_t lookup_smem_bytes() {
 }
 
 template <int R, bool SPLIT>
-static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, float2* c2, float* out_f32, __half* out_hi,
-                             __half* out_lo, int out_stride, int npix, cudaStream_t s, const Fh2Gather& gat) {
+static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, const float2* c2, float* out_f32, __half* out_hi,
+                             __half* out_lo, int out_stride, int npix, cudaStream_t s) {
   static PerDeviceOnce attr_set;
   const size_t smem = lookup_smem_bytes<R>();
   int dev = 0, rc_dev;
@@ -659,7 +659,7 @@ static int launch_lookup_cfg(const PyramidView& pv, const PyramidMaps& maps, flo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix, gat));
+  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_kernel<R, SPLIT>, pv, maps, c2, out_f32, out_hi, out_lo, out_stride, npix));
   RB_CHECK_LAUNCH("corr_lookup_kernel");
   return RB_OK;
 }
@@ -692,9 +692,8 @@ static int launch_lookup_v5(const PyramidView& pv, const PyramidMapsV5& maps, co
   return RB_OK;
 }
 
-// apply_delta != nullptr: coords is READ-WRITE -- the kernel first adds the pending flow update to it (Fh2Gather, common.cuh)
 int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
-                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s, const Fh2Gather* apply_delta) {
+                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s) {
   PyramidView pv;
   int rc = pyramid_view(pyramid, B, h, w, &pv);
   if (rc) return rc;
@@ -703,9 +702,6 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
              out_stride);
   const int npix = B * h * w;
   const float2* c2 = reinterpret_cast<const float2*>(coords);
-  float2* c2rw = const_cast<float2*>(c2);  // written only when apply_delta is set (the caller passed a mutable buffer)
-  Fh2Gather gat{nullptr, nullptr, 0, h, w};
-  if (apply_delta) gat = *apply_delta;
   const bool split = out_hi != nullptr;
   // Default: corr_lookup_kernel (block = 16 px x 4 levels, thread = window row).  RAFT_B200_LOOKUP_V5=1 selects the
   // warp-per-pixel kernel (lane = tap) that the volume-free path is built on: same DRAM traffic, 29 % shared-memory bank
@@ -713,7 +709,7 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
   // (profiles/r02_notes.md), kept selectable because it shares every line with the volume-free instantiation.
   static const bool v5 = getenv("RAFT_B200_LOOKUP_V5") != nullptr;
   const bool f32_rows_ok = split || (out_stride % 4 == 0 && reinterpret_cast<uintptr_t>(out_f32) % 16 == 0);
-  if (v5 && f32_rows_ok && !apply_delta) {
+  if (v5 && f32_rows_ok) {
     PyramidMapsV5 maps;
     memset(&maps, 0, sizeof(maps));
     for (int l = 0; l < RB_NUM_LEVELS; ++l) {
@@ -738,14 +734,14 @@ int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __h
     if (!pv.tma_ok[l]) continue;
     uint64_t dims[3] = {(uint64_t)pv.wl[l], (uint64_t)pv.hl[l], (uint64_t)npix};
     uint64_t str[2] = {(uint64_t)pv.wl[l] * 4, (uint64_t)pv.wl[l] * pv.hl[l] * 4};
-    uint32_t box[3] = {(uint32_t)kPatchCols, (uint32_t)(2 * radius + 3), 1};
+    uint32_t box[3] = {(uint32_t)kPatchCols, (uint32_t)(2 * radius + 2), 1};
     if (cached_tmap(&maps.m[l], pv.base[l], 3, dims, str, box, tc::TMAP_F32_SW64) != RB_OK) pv.tma_ok[l] = 0;  // plain loads instead
   }
   if (radius == 4)
-    return split ? launch_lookup_cfg<4, true>(pv, maps, c2rw, nullptr, out_hi, out_lo, out_stride, npix, s, gat)
-                 : launch_lookup_cfg<4, false>(pv, maps, c2rw, out_f32, nullptr, nullptr, out_stride, npix, s, gat);
-  return split ? launch_lookup_cfg<3, true>(pv, maps, c2rw, nullptr, out_hi, out_lo, out_stride, npix, s, gat)
-               : launch_lookup_cfg<3, false>(pv, maps, c2rw, out_f32, nullptr, nullptr, out_stride, npix, s, gat);
+    return split ? launch_lookup_cfg<4, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
+                 : launch_lookup_cfg<4, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
+  return split ? launch_lookup_cfg<3, true>(pv, maps, c2, nullptr, out_hi, out_lo, out_stride, npix, s)
+               : launch_lookup_cfg<3, false>(pv, maps, c2, out_f32, nullptr, nullptr, out_stride, npix, s);
 }
 
 // ---- F2: volume-free correlation ---------------------------------------------------------------------------------------------
@@ -875,7 +871,7 @@ extern "C" int rb_corr_lookup(const float* pyramid, const float* coords, float* 
   RB_REQUIRE(pyramid && coords && out, RB_ERR_BAD_ARG, "rb_corr_lookup: null pointer");
   RB_REQUIRE(B > 0 && h > 0 && w > 0, RB_ERR_BAD_SHAPE, "rb_corr_lookup: bad shape");
   int K = (2 * radius + 1) * (2 * radius + 1);
-  return launch_lookup(pyramid, coords, out, nullptr, nullptr, 4 * K, B, h, w, radius, (cudaStream_t)stream, nullptr);
+  return launch_lookup(pyramid, coords, out, nullptr, nullptr, 4 * K, B, h, w, radius, (cudaStream_t)stream);
 }
 
 /* ---- F2: volume-free correlation; same results as rb_corr_build + rb_corr_lookup up to fp32 summation order ---- */

@@ -10,6 +10,7 @@
 //           (tests/test_gpu_fullsize.py::test_pyramid_levels_are_valid_avgpools_fullsize, tests/test_oracle.py::test_pool_linearity_valid_floor).
 // The GEMMs reuse the implicit-GEMM kernel of conv_tc.cu with a 1x1 "filter" whose weight operand
 // is the (pooled) fmap2 of the same batch element.
+#include <math.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -136,7 +137,14 @@ int corr_build_tc(const float* fmap1, const float* fmap2, float* pyramid, int B,
     p.w_hi = W.f2_hi[l]; p.w_lo = W.f2_lo[l]; p.bias = nullptr;
     p.cout = rows; p.cout_pad = rows_pad; p.kh = 1; p.kw = 1; p.w_per_batch = 1;
     p.B = B; p.h = h; p.w = w;
-    p.epi = EPI_F32; p.scale = 1.f; p.div = sqrtf((float)C);  // divide after the matmul (:213)
+    p.epi = EPI_F32;
+    {  // divide after the matmul (:213).  sqrt(256) = 16: the division is an exact scaling, a multiply gives the same bits
+      const float sq = sqrtf((float)C);
+      int e;
+      const bool pow2 = frexpf(sq, &e) == 0.5f;
+      p.scale = pow2 ? 1.0f / sq : 1.f;
+      p.div = pow2 ? 0.f : sq;
+    }
     p.f0 = pyramid + lvl_off;
     int rc = launch_conv_tc(p, s);
     if (rc) return rc;

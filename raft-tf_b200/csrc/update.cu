@@ -22,8 +22,7 @@
 namespace rb {
 
 int launch_lookup(const float* pyramid, const float* coords, float* out_f32, __half* out_hi,
-                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s,
-                  const Fh2Gather* apply_delta = nullptr);
+                  __half* out_lo, int out_stride, int B, int h, int w, int radius, cudaStream_t s);
 int launch_lookup_otf(const float* fmap1, const float* fmap2, const float* pooled, const float* coords, float* out_f32,
                       __half* out_hi, __half* out_lo, int out_stride, int B, int h, int w, int C, int radius, cudaStream_t s);
 
@@ -460,9 +459,10 @@ static int launch_flow_head2(const ConvParams& p, cudaStream_t s) {
 // G[q][s][tap*2+o] = sum over the part's channels of relu(conv1)[q][c] * W2[tap][c][o].  The 3x3 conv (SAME: zero outside
 // the image) is then  delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o]  -- fixed summation order
 // (tap-major, parts ascending): bit-reproducible, batched == per-sample.  coords1 += delta (RAFT.py:102).
-// Stand-alone form (rb_update_step, and the last iteration of rb_raft_iterate): one warp per pixel, fh2_delta_warp of
-// common.cuh.  Inside the loop the NEXT iteration's lookup kernel applies the delta itself (corr.cu), which removes this
-// launch and one kernel boundary from the dependent chain of every iteration.
+// One warp per pixel (fh2_delta_warp, common.cuh).  Letting the NEXT iteration's lookup kernel apply the delta itself
+// (no launch of its own, one kernel boundary less on the dependent chain) was built and measured in round 2: +12 us per
+// iteration -- the lookup's critical path grows by the gather, and the flow branch (flow_conv7 -> convf2) can then only
+// fork after the lookup instead of beside it (profiles/r02_notes.md).
 __global__ void __launch_bounds__(256) fh2_gather_kernel(const Fh2Gather g, float* coords1, float* delta_out, int B) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -563,13 +563,9 @@ static int side_stream(SideStream** out) {
   return RB_OK;
 }
 
-// pyramid != nullptr: the lookup for this iteration is issued here too (on the main branch).
-// delta_in: coords1 still lacks the previous step's delta -- this step's lookup kernel applies it (needs pyramid);
-// defer_delta: leave THIS step's delta in W.fh2_part for the next step's lookup (only honoured when the conv2 fold is on;
-// *deferred reports what happened).
+// pyramid != nullptr: the lookup for this iteration is issued here too (on the main branch)
 static int update_step(const Variant& v, const void* blob, void* wsp, float* coords1, float* delta_out,
-                       float* mask_out, int B, int h, int w, cudaStream_t s, const float* pyramid = nullptr,
-                       bool delta_in = false, bool defer_delta = false, bool* deferred = nullptr) {
+                       float* mask_out, int B, int h, int w, cudaStream_t s, const float* pyramid = nullptr) {
   const size_t npix = (size_t)B * h * w;
   const PackedLayout L = packed_layout(v);
   const Workspace W = workspace_layout(v, npix, wsp);
@@ -594,13 +590,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   // ---- motion encoder (model_utils.py:110-129) ----
   SideStream* ss;
   if ((rc = side_stream(&ss))) return rc;
-  if (deferred) *deferred = false;
   const float* fh2_bias = reinterpret_cast<const float*>(bb + L.bias[P_FH2]);
-  if (delta_in) {  // the lookup applies the pending delta and rewrites coords1: the flow branch may only fork after it
-    RB_REQUIRE(pyramid, RB_ERR_BAD_ARG, "internal: a pending delta needs the lookup of this step");
-    Fh2Gather g{W.fh2_part, fh2_bias, L.cout[P_FH1] / 16, h, w};
-    if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s, &g))) return rc;
-  }
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
   {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
@@ -630,7 +620,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     RB_CHECK_CUDA(cudaEventRecord(ss->join, ss->stream));
   }
   // correlation branch (main stream): [lookup ->] convc1 [-> convc2]
-  if (pyramid && !delta_in) {
+  if (pyramid) {
     if ((rc = launch_lookup(pyramid, coords1, nullptr, W.corr.hi, W.corr.lo, v.corr_pad, B, h, w, v.radius, s))) return rc;
   }
 #ifdef RB_EXPERIMENTS
@@ -718,12 +708,8 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     }
     if ((rc = launch_conv_dbg(p, s))) return rc;
     if (fuse) {
-      if (defer_delta && !delta_out) {
-        if (deferred) *deferred = true;  // the next step's lookup kernel adds it to coords1
-      } else {
-        Fh2Gather g{W.fh2_part, fh2_bias, p.fh2_parts, h, w};
-        if ((rc = launch_fh2_gather(g, coords1, delta_out, B, s))) return rc;
-      }
+      Fh2Gather g{W.fh2_part, fh2_bias, p.fh2_parts, h, w};
+      if ((rc = launch_fh2_gather(g, coords1, delta_out, B, s))) return rc;
     } else {
       p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
       p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
@@ -975,16 +961,9 @@ extern "C" int rb_raft_iterate(int small, const void* weights, void* workspace, 
   int rc = check_shape("rb_raft_iterate", B, h, w);
   if (rc) return rc;
   const Variant& v = variant(small);
-  // RAFT_B200_NO_DELTA_FUSE=1: every step launches its own gather kernel (A/B knob)
-  static const bool no_defer = getenv("RAFT_B200_NO_DELTA_FUSE") != nullptr;
-  bool pending = false;
   for (int it = 0; it < iters; ++it) {
     float* m = (it == iters - 1 && !small) ? mask_out : nullptr;
-    bool deferred = false;
-    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream, pyramid, pending,
-                          !no_defer && it + 1 < iters, &deferred)))
-      return rc;
-    pending = deferred;
+    if ((rc = update_step(v, weights, workspace, coords1, nullptr, m, B, h, w, (cudaStream_t)stream, pyramid))) return rc;
   }
   return RB_OK;
 }
