@@ -50,6 +50,11 @@ const char* rb_last_error(void);
 /* Select the back end for subsequent calls on this thread (default RB_MATH_TC). */
 int rb_set_math_mode(int mode);
 int rb_get_math_mode(void);
+/* Device selection.  The library carries its own CUDA runtime instance; its per-thread current device does not follow the
+ * host framework's (torch.cuda.device(...), cudaSetDevice in another runtime).  Call this when the calling thread switches
+ * GPUs, before the calls that enqueue work (their stream argument 0 = "default stream of the current device").
+ * One process per GPU (torchrun) never needs it. */
+int rb_set_device(int device);
 /* Number of kernels this library has launched on the calling thread since the last reset. */
 long long rb_launch_count(void);
 void rb_launch_count_reset(void);

@@ -44,5 +44,12 @@ extern "C" int rb_set_math_mode(int mode) {
   return RB_OK;
 }
 extern "C" int rb_get_math_mode(void) { return rb::g_mode; }
+// The library links its own (static) CUDA runtime, whose per-thread "current device" is independent of the host
+// framework's: a caller that drives several GPUs from one thread tells the library which one the following calls (and their
+// stream handles -- stream 0 means "the current device's default stream") belong to.  raft_b200/capi.py does this in stream().
+extern "C" int rb_set_device(int device) {
+  RB_CHECK_CUDA(cudaSetDevice(device));
+  return RB_OK;
+}
 extern "C" long long rb_launch_count(void) { return rb::g_launches; }
 extern "C" void rb_launch_count_reset(void) { rb::g_launches = 0; }

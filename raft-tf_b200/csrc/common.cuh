@@ -84,10 +84,7 @@ enum Epilogue : int {
   EPI_ZR = 1,     // c<hidden: z=sigmoid -> f0 ; else r=sigmoid, r*h(f1) -> d0
   EPI_Q = 2,      // q=tanh ; h=(1-z)h+zq -> f1 and d0
   EPI_DELTA = 3,  // c<2: coords1(f1)[c] += v ; optional copy to f2
-  EPI_F32 = 4,    // f0[pix*cout+c] = scale*v
-  EPI_FH2 = 5     // flow_head/conv1 with conv2 folded in (tensor-core back end only): y = relu(acc+bias) is NOT stored; each
-                  // epilogue thread forms, per 16-channel group, the 18 dot products <y[c..c+16), W2[tap][c..][o]> ->
-                  // fh2_part[pix][c/16][tap*2+o]; fh2_gather_kernel (update.cu) sums parts and 3x3 neighbours
+  EPI_F32 = 4     // f0[pix*cout+c] = scale*v
 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1 };
 
@@ -106,9 +103,6 @@ struct ConvParams {
   const float* flow_tail;  // EPI_ACT, 16-channel epilogue: coords1; the last two channels are written as flow = coords1 - grid
   double* stat_part;  // EPI_F32 + tensor-core wide epilogue: per-(sample, strip, channel) sum / sum of squares of the
   int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
-  const float* fh2_w;  // EPI_FH2: fp32 [cout][20] = flow_head/conv2 weights W2[tap][c][o] at [c][tap*2+o] (18 used), per OUTPUT channel c of this conv
-  float* fh2_part;     // EPI_FH2: [pixel][fh2_parts][18] partial dot products; part = output channel / 16
-  int fh2_parts;
   int stash;      // 1: single-tile CTAs park the gate epilogues' fp32 operands in spare TMEM columns during the MMA loop
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue
@@ -526,35 +520,6 @@ __device__ __forceinline__ void warp_stats16(const float* y, float& s, float& s2
   s = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
   s2 = b[0] + __shfl_xor_sync(0xffffffffu, b[0], 1);
   ch = (int)(((lane >> 4) & 1u) * 8u + ((lane >> 3) & 1u) * 4u + ((lane >> 2) & 1u) * 2u + ((lane >> 1) & 1u));
-}
-
-// ---- flow_head/conv2 folded into conv1 (EPI_FH2): the 3x3 gather over the per-pixel partial products -------------------
-// G[q][s][tap*2+o] (s = 16-channel group of conv1's output) -> delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o],
-// zero outside the image (SAME padding of conv1's activations).  One WARP per pixel: item = tap * parts + s is spread over
-// the lanes (ascending per lane), then a fixed xor butterfly: the summation order is a function of `parts` only, so the
-// stand-alone kernel (update.cu) and the lookup kernel that applies the delta itself (corr.cu) give identical bits.
-struct Fh2Gather {
-  const float* part;  // nullptr: nothing to apply
-  const float* bias;  // [2]
-  int parts, h, w;
-};
-__device__ __forceinline__ float2 fh2_delta_warp(const Fh2Gather& g, int b, int y, int x, int lane) {
-  float d0 = 0.f, d1 = 0.f;
-  for (int it = lane; it < 9 * g.parts; it += 32) {
-    const int t = it / g.parts, s = it - t * g.parts;
-    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-    if (yy >= 0 && yy < g.h && xx >= 0 && xx < g.w) {
-      const float2 v = *reinterpret_cast<const float2*>(g.part + ((size_t)((b * g.h + yy) * g.w + xx) * g.parts + s) * 18 + t * 2);
-      d0 += v.x;
-      d1 += v.y;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-  }
-  return make_float2(d0 + g.bias[0], d1 + g.bias[1]);
 }
 
 // back ends

@@ -55,9 +55,7 @@ struct TcCfg {
 // the weight-tile requests (the measured bound of the MMA loop is the ~38 B/clk a single SM can request from L2).
 // EXTRAS: phase timestamps (p.dbg) and fused instance-norm statistics (p.stat_part) -- a separate instantiation, so that
 // the kernel the update block runs stays below the 96-register cap of a 576-thread CTA without spills.
-// FH2: flow_head/conv1 with flow_head/conv2 folded into its epilogue (EPI_FH2, see common.cuh) -- its own instantiation
-// (18 extra accumulators per epilogue thread must not cost the shared kernel registers).
-template <int BLOCK_N, bool PAIR, bool EXTRAS, bool FH2 = false>
+template <int BLOCK_N, bool PAIR, bool EXTRAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -70,7 +68,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* w2s = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256);  // FH2: [BLOCK_N][20] fp32, 16-byte aligned rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = (EXTRAS && p.dbg) ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
@@ -225,10 +222,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (grp < Cfg::kGroups) {
       asm volatile("griddepcontrol.wait;" ::: "memory");  // addend / z / h reads and all stores come after the predecessor
       int li = 0;
-      int staged_nt = -1;
       // ---- operand stash (see common.cuh): single-tile CTAs of the GRU gate convs, while the MMA loop runs ----
       uint32_t stash_row = 0;
-      if constexpr (!FH2 && !EXTRAS && BLOCK_N >= 32) {
+      if constexpr (!EXTRAS && BLOCK_N >= 32) {
         const int nops = p.epi == EPI_Q ? 3 : 2;
         if (p.stash && wide && (p.epi == EPI_ZR || p.epi == EPI_Q) && g.total_tiles <= (int)gridDim.x &&
             Cfg::kAccCols + nops * BLOCK_N <= Cfg::kTmemCols && first < g.total_tiles) {
@@ -277,18 +273,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const bool valid = (py < p.h) && (px < p.w) && (mt < g.m_tiles);
         const int pix = (b * p.h + py) * p.w + px;
         const int ab = li & 1;
-        if constexpr (FH2) {
-          if (staged_nt != nt) {  // all epilogue warps walk the same tile sequence: the named barrier is uniform
-            if (staged_nt >= 0) asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroups * 128) : "memory");  // previous rows no longer read
-            const int et = (warp - 2) * 32 + lane;  // 0 .. kGroups*128-1 (warps 2.. are the live epilogue warps: grp < kGroups)
-            const float4* src = reinterpret_cast<const float4*>(p.fh2_w + (size_t)n0 * 20);
-            float4* dst = reinterpret_cast<float4*>(w2s);
-            const int rows = min(BLOCK_N, p.cout - n0);
-            for (int e = et; e < rows * 5; e += Cfg::kGroups * 128) dst[e] = __ldg(src + e);
-            asm volatile("bar.sync 1, %0;" ::"r"(Cfg::kGroups * 128) : "memory");
-            staged_nt = nt;
-          }
-        }
         mbar_wait_warp(&tmem_full_bar[ab], (li >> 1) & 1);
         tc_fence_after();
         if (li == 0) {
@@ -307,35 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
-          if constexpr (FH2) {
-            // y = relu(acc + bias) (model_utils.py:133), then this thread's share of conv2 (model_utils.py:134):
-            // acc2[tap*2+o] += y[c] * W2[tap][c][o] in fp32; the weights row of a channel is one broadcast 80-byte read
-            // One partial per 16-CHANNEL GROUP (part = channel / 16), whatever the tile width: the summation partition must
-            // not depend on the launch geometry, or a batched run would differ from the per-sample runs in the last bit.
-            float bsv[16], acc2[18];
-            ld256_nc(p.bias + n0 + c, bsv);
-            ld256_nc(p.bias + n0 + c + 8, bsv + 8);
-#pragma unroll
-            for (int i = 0; i < 18; ++i) acc2[i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float y = fmaxf(v[i] + bsv[i], 0.f);
-              const float4* wr = reinterpret_cast<const float4*>(w2s + (size_t)(c + i) * 20);
-              const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
-              const float2 w4 = *reinterpret_cast<const float2*>(wr + 4);
-              acc2[0] = fmaf(y, w0.x, acc2[0]); acc2[1] = fmaf(y, w0.y, acc2[1]); acc2[2] = fmaf(y, w0.z, acc2[2]); acc2[3] = fmaf(y, w0.w, acc2[3]);
-              acc2[4] = fmaf(y, w1.x, acc2[4]); acc2[5] = fmaf(y, w1.y, acc2[5]); acc2[6] = fmaf(y, w1.z, acc2[6]); acc2[7] = fmaf(y, w1.w, acc2[7]);
-              acc2[8] = fmaf(y, w2.x, acc2[8]); acc2[9] = fmaf(y, w2.y, acc2[9]); acc2[10] = fmaf(y, w2.z, acc2[10]); acc2[11] = fmaf(y, w2.w, acc2[11]);
-              acc2[12] = fmaf(y, w3.x, acc2[12]); acc2[13] = fmaf(y, w3.y, acc2[13]); acc2[14] = fmaf(y, w3.z, acc2[14]); acc2[15] = fmaf(y, w3.w, acc2[15]);
-              acc2[16] = fmaf(y, w4.x, acc2[16]); acc2[17] = fmaf(y, w4.y, acc2[17]);
-            }
-            if (valid) {
-              float2* dst = reinterpret_cast<float2*>(p.fh2_part + ((size_t)pix * p.fh2_parts + ((n0 + c) >> 4)) * 18);
-#pragma unroll
-              for (int i = 0; i < 9; ++i) dst[i] = make_float2(acc2[2 * i], acc2[2 * i + 1]);
-            }
-          }
-          if (!FH2 && (valid || stash_row != 0)) {  // with a stash the TMEM reads inside are warp-collective: all lanes go
+          if (valid || stash_row != 0) {  // with a stash the TMEM reads inside are warp-collective: all lanes go
             if (wide) {
               epilogue_wide16(p, pix, n0 + c, v, Stash{stash_row, BLOCK_N, c}, valid);
             } else {
@@ -343,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               epilogue_store<8>(p, pix, n0 + c + 8, v + 8);
             }
           }
-          if (!FH2 && EXTRAS && p.stat_part) {  // instance-norm statistics of the values just stored (v was finalised in place; host: wide only)
+          if (EXTRAS && p.stat_part) {  // instance-norm statistics of the values just stored (v was finalised in place; host: wide only)
             if (!valid) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -515,42 +471,6 @@ static int choose_block_n(int cout, long m_tiles, int ctas = 148) {  // ctas: pe
   return best;
 }
 
-// EPI_FH2 launches (flow_head/conv1 + folded conv2): the FH2 instantiation, ring + [BLOCK_N][20] fp32 of conv2 weights.
-template <int BLOCK_N>
-static int launch_fh2(const ConvParams& p, const TileGeom& g, const CUtensorMap* maps, int num_sms, cudaStream_t s) {
-  using Cfg = TcCfg<BLOCK_N>;
-  constexpr int kSmem = Cfg::kSmemBytes + BLOCK_N * 80;
-  static_assert(kSmem <= 227 * 1024, "FH2: shared memory");
-  static PerDeviceOnce attr_set;
-  int dev = 0, rc_dev;
-  if ((rc_dev = current_device(&dev))) return rc_dev;
-  if (!attr_set.test(dev)) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set.set(dev);
-  }
-  RB_REQUIRE(p.fh2_w && p.fh2_part && p.fh2_parts == p.cout / 16 && p.cout % 16 == 0 && p.bias && !p.addend &&
-                 (reinterpret_cast<uintptr_t>(p.bias) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.fh2_w) & 15) == 0,
-             RB_ERR_BAD_ARG, "conv_tc: EPI_FH2 launch is inconsistent (parts %d, cout %d)", p.fh2_parts, p.cout);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  int units = num_sms;
-  if (p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;
-  cfg.gridDim = dim3(g.total_tiles < units ? g.total_tiles : units);
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = kSmem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
-  cfg.numAttrs = pdl;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false, false, true>, maps[0], maps[1], maps[2], maps[3], p, g, Cfg::kStages));
-  RB_CHECK_LAUNCH("conv_tc_kernel<FH2>");
-  return RB_OK;
-}
-int conv_tc_fh2_parts(const ConvParams& p);  // parts of fh2_part an EPI_FH2 launch produces
-
 template <int BLOCK_N, bool PAIR>
 static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = TcCfg<BLOCK_N>;
@@ -566,7 +486,6 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
   g.m_tiles = p.B * g.tiles_x * g.tiles_y;
   g.total_tiles = (PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
-  if (p.epi == EPI_FH2) return launch_fh2<BLOCK_N>(p, g, maps, num_sms, s);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   int units = PAIR ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
@@ -636,8 +555,6 @@ int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
   return RB_OK;
 }
 #endif
-
-int conv_tc_fh2_parts(const ConvParams& p) { return p.cout / 16; }  // one partial per 16-channel group (EPI_FH2)
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
 #ifdef RB_EXPERIMENTS

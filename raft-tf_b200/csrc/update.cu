@@ -84,7 +84,6 @@ struct PackedLayout {
   size_t hi[P_COUNT], lo[P_COUNT], bias[P_COUNT];  // byte offsets
   int cout[P_COUNT], cout_pad[P_COUNT], kh[P_COUNT], kw[P_COUNT];
   size_t f1_w, f1_b;  // convf1: fp32 [49*2][cout] and bias
-  size_t fh2_w;       // flow_head/conv2 as fp32 [fh][20]: W2[tap][c][o] at [c][tap*2+o] (18 used) -- EPI_FH2 epilogue of conv1
   size_t total;
 };
 
@@ -109,7 +108,6 @@ static PackedLayout packed_layout(const Variant& v) {
   const RefConv& f = v.ref[v.convf1_ref];
   L.f1_w = off; off = align_up(off + (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float), 256);
   L.f1_b = off; off = align_up(off + (size_t)f.cout * sizeof(float), 256);
-  L.fh2_w = off; off = align_up(off + (size_t)v.fh * 20 * sizeof(float), 256);
   L.total = off;
   return L;
 }
@@ -121,10 +119,8 @@ struct Workspace {
   float* Z;
   float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
   unsigned int* counters;  // grid-barrier counters of the fused update-step kernel (update_fused.cu)
-  float* fh2_part;         // [npix][kFh2MaxParts][18]: per-pixel partial products of the folded flow_head/conv2 (EPI_FH2)
   size_t total;
 };
-constexpr int kFh2MaxParts = 16;
 
 static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
   Workspace W;
@@ -157,8 +153,6 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
   }
   W.counters = reinterpret_cast<unsigned int*>(b + off);
   off += 1024;
-  W.fh2_part = reinterpret_cast<float*>(b + off);
-  off += align_up(npix * (size_t)kFh2MaxParts * 18 * sizeof(float), 1024);
   W.total = off;
   return W;
 }
@@ -455,48 +449,6 @@ static int launch_flow_head2(const ConvParams& p, cudaStream_t s) {
   return RB_OK;
 }
 
-// flow_head/conv2 folded into conv1 (EPI_FH2): conv1's epilogue left, per pixel q and part s (cout tile x column group),
-// G[q][s][tap*2+o] = sum over the part's channels of relu(conv1)[q][c] * W2[tap][c][o].  The 3x3 conv (SAME: zero outside
-// the image) is then  delta[p][o] = b[o] + sum_tap sum_s G[p + (ky-1, kx-1)][s][tap][o]  -- fixed summation order
-// (tap-major, parts ascending): bit-reproducible, batched == per-sample.  coords1 += delta (RAFT.py:102).
-// One warp per pixel (fh2_delta_warp, common.cuh).  Letting the NEXT iteration's lookup kernel apply the delta itself
-// (no launch of its own, one kernel boundary less on the dependent chain) was built and measured in round 2: +12 us per
-// iteration -- the lookup's critical path grows by the gather, and the flow branch (flow_conv7 -> convf2) can then only
-// fork after the lookup instead of beside it (profiles/r02_notes.md).
-__global__ void __launch_bounds__(256) fh2_gather_kernel(const Fh2Gather g, float* coords1, float* delta_out, int B) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= B * g.h * g.w) return;  // warp-uniform
-  const float2 d = fh2_delta_warp(g, i / (g.w * g.h), (i / g.w) % g.h, i % g.w, lane);
-  if (lane == 0) {
-    float2 c = *reinterpret_cast<float2*>(coords1 + (size_t)i * 2);
-    c.x += d.x; c.y += d.y;  // RAFT.py:102
-    *reinterpret_cast<float2*>(coords1 + (size_t)i * 2) = c;
-    if (delta_out) *reinterpret_cast<float2*>(delta_out + (size_t)i * 2) = d;
-  }
-}
-
-static int launch_fh2_gather(const Fh2Gather& g, float* coords1, float* delta_out, int B, cudaStream_t s) {
-  const int h = g.h, w = g.w;
-  static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((B * h * w + 7) / 8);
-  cfg.blockDim = dim3(256);
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl;
-  RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fh2_gather_kernel, g, coords1, delta_out, B));
-  RB_CHECK_LAUNCH("fh2_gather_kernel");
-  return RB_OK;
-}
-
-int conv_tc_fh2_parts(const ConvParams& p);
-
 // Phase-timestamp debug buffer (tools/phase_times.py): rb_debug_set_buffer(ptr, convs) makes the next update
 // step record 8 timestamps per CTA for each of its convs, in launch order, 4096 CTAs per conv.
 static thread_local long long* g_dbg = nullptr;
@@ -590,7 +542,6 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   // ---- motion encoder (model_utils.py:110-129) ----
   SideStream* ss;
   if ((rc = side_stream(&ss))) return rc;
-  const float* fh2_bias = reinterpret_cast<const float*>(bb + L.bias[P_FH2]);
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
   {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
@@ -690,38 +641,23 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     if ((rc = launch_conv_dbg(p, s))) return rc;
   }
   // ---- flow head (model_utils.py:131-135) + coords1 += delta (RAFT.py:102) ----
+  // conv2 (3x3, fh -> 2) runs as an N = 16 implicit GEMM on 55 CTAs (~15 us at batch 1).  Folding it into conv1's epilogue
+  // (18 per-pixel dot products per 16-channel group + a gather kernel, no FH store) was built in round 2: parity-green and
+  // 2.2 % SLOWER per iteration at batch 1, 5 % at batch 8 (same-box ABAB, profiles/r02_notes.md) -- removed again.
   {
     ConvParams p = base_params(v, L, blob, P_FH1, W.hx, v.hx, 0, B, h, w);
     set_act(p, ACT_RELU, W.fh, v.fh, 0);
-    // Default (tensor-core back end): conv2 (3x3, fh -> 2: as an implicit GEMM it used 2 of 16 MMA columns for ~15 us per
-    // iteration at batch 1) is folded into conv1's epilogue + a tiny gather kernel; conv1's activations are never stored.
-    // RAFT_B200_NO_FH2_FUSE=1: the two separate convs (A/B knob; also what the CUDA-core back end runs).
-    static const bool no_fuse = getenv("RAFT_B200_NO_FH2_FUSE") != nullptr;
-    bool fuse = !fused && !no_fuse && !g_dbg && math_mode() == RB_MATH_TC && p.cout % 16 == 0 && L.kh[P_FH2] == 3 && L.kw[P_FH2] == 3;
-    if (fuse) {
-      p.epi = EPI_FH2;
-      p.fh2_w = reinterpret_cast<const float*>(bb + L.fh2_w);
-      p.fh2_part = W.fh2_part;
-      p.fh2_parts = conv_tc_fh2_parts(p);
-      fuse = p.fh2_parts <= kFh2MaxParts;
-      if (!fuse) set_act(p, ACT_RELU, W.fh, v.fh, 0);
-    }
     if ((rc = launch_conv_dbg(p, s))) return rc;
-    if (fuse) {
-      Fh2Gather g{W.fh2_part, fh2_bias, p.fh2_parts, h, w};
-      if ((rc = launch_fh2_gather(g, coords1, delta_out, B, s))) return rc;
-    } else {
-      p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
-      p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
-      // RAFT_B200_FH2_SIMT=1: CUDA-core kernel instead of the N=16 implicit GEMM (profiles/r01_notes.md) -> opt-in.
-      static const bool fh2_simt = getenv("RAFT_B200_FH2_SIMT") != nullptr;
-      const bool direct = !fused && fh2_simt && p.kh == 3 && p.kw == 3 && p.in_choff == 0 && p.in_stride % 8 == 0 &&
-                          (p.cin_pad == 256 || p.cin_pad == 128) && p.cout == 2;
-      if (direct) {
-        if ((rc = launch_flow_head2(p, s))) return rc;
-      } else if ((rc = launch_conv_dbg(p, s))) {
-        return rc;
-      }
+    p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
+    p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
+    // RAFT_B200_FH2_SIMT=1: CUDA-core kernel instead of the N=16 implicit GEMM (profiles/r01_notes.md) -> opt-in.
+    static const bool fh2_simt = getenv("RAFT_B200_FH2_SIMT") != nullptr;
+    const bool direct = !fused && fh2_simt && p.kh == 3 && p.kw == 3 && p.in_choff == 0 && p.in_stride % 8 == 0 &&
+                        (p.cin_pad == 256 || p.cin_pad == 128) && p.cout == 2;
+    if (direct) {
+      if ((rc = launch_flow_head2(p, s))) return rc;
+    } else if ((rc = launch_conv_dbg(p, s))) {
+      return rc;
     }
   }
   // ---- mask head (model_utils.py:180-183); only the last iteration's mask is ever consumed ----
@@ -838,18 +774,6 @@ extern "C" int rb_update_weights_pack(int small, const float* const* W_host, con
     const RefConv& f = v.ref[v.convf1_ref];
     memcpy(host.data() + L.f1_w, W_host[v.convf1_ref], (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float));
     memcpy(host.data() + L.f1_b, b_host[v.convf1_ref], (size_t)f.cout * sizeof(float));
-  }
-  {  // flow_head/conv2 [3,3,fh,2] HWIO -> fp32 [fh][20], entry [c][tap*2+o]
-    int fh2_ref = -1;
-    for (int i = 0; i < v.nref; ++i)
-      if (strstr(v.ref[i].name, "flow_head/conv2")) fh2_ref = i;
-    RB_REQUIRE(fh2_ref >= 0 && v.ref[fh2_ref].cin == v.fh && v.ref[fh2_ref].cout == 2 && v.ref[fh2_ref].kh == 3, RB_ERR_BAD_SHAPE,
-               "internal: flow_head/conv2 shape");
-    float* dst = reinterpret_cast<float*>(host.data() + L.fh2_w);
-    const float* W2 = W_host[fh2_ref];
-    for (int t = 0; t < 9; ++t)
-      for (int c = 0; c < v.fh; ++c)
-        for (int o = 0; o < 2; ++o) dst[(size_t)c * 20 + t * 2 + o] = W2[((size_t)t * v.fh + c) * 2 + o];
   }
   cudaStream_t s = (cudaStream_t)stream;
   RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), L.total, cudaMemcpyHostToDevice, s));

@@ -24,6 +24,7 @@ SIGNATURES = {
     "rb_last_error": (C.c_char_p, []),
     "rb_set_math_mode": (_i, [_i]),
     "rb_get_math_mode": (_i, []),
+    "rb_set_device": (_i, [_i]),
     "rb_launch_count": (C.c_longlong, []),
     "rb_launch_count_reset": (None, []),
     "rb_debug_set_buffer": (_i, [_vp]),
@@ -90,8 +91,20 @@ def ptr(t):
     return t.data_ptr()
 
 
+import threading
+
+_tls = threading.local()
+
+
 def stream():
+    """Current torch stream handle for the enqueueing calls.  Also keeps the library's own CUDA runtime (statically linked:
+    its per-thread current device is independent of torch's) on torch's current device -- every call that launches work
+    takes stream() as an argument, so this is the one place that needs to know."""
     import torch
+    dev = torch.cuda.current_device()
+    if getattr(_tls, "device", None) != dev:
+        check(lib.rb_set_device(dev))
+        _tls.device = dev
     return torch.cuda.current_stream().cuda_stream
 
 
