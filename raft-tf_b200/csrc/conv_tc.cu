@@ -26,7 +26,6 @@ using namespace tc;
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled row
-constexpr int kATileBytes = kTileM * 128;  // 16 KB
 constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 
 // PERSISTENT kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so CTAs that
@@ -38,8 +37,8 @@ constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 // A operand: one pipeline stage holds the hi and lo planes of ONE activation box of (bw + hx - 1) x bh pixels x 64 channels.
 // When the pixel tile is a single image row (bh = 1: every grid at least 128 wide) the taps of one filter ROW are 1-pixel
 // shifts of the same row, so the box is fetched ONCE per (chunk, ky) with a halo of kw - 1 pixels (hx = kw) and tap kx is
-// the UMMA descriptor of the same shared-memory tile advanced by kx rows of 128 bytes (matrix base offset = kx & 7: the
-// start is no longer aligned to the 1024-byte repeat of the 128-byte swizzle).  The activation traffic of 3x3 / 1x5 convs
+// the UMMA descriptor of the same shared-memory tile advanced by kx rows of 128 bytes (the start is then no longer aligned
+// to the 1024-byte repeat of the 128-byte swizzle, which is fine: see the MMA loop).  The activation traffic of 3x3 / 1x5 convs
 // drops 3x / 5x -- the N <= 96 tiles are bound by the ~58 B/clk an SM ingests through TMA, not by the tensor pipe
 // (profiles/r01_notes.md, r02_notes.md).  Weight tiles ([B_hi ; B_lo], one per tap) travel through a ring of their own.
 constexpr int kAPlaneBytes = 17 * 1024;  // >= (128 + 4) rows x 128 B, 1024-byte multiple (swizzle repeat)
@@ -196,9 +195,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int t = 0; t < hx; ++t) {
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
-            // tap t of the row: the same tile, t pixel rows (128 B each) further; base offset = row phase inside the swizzle repeat
-            const uint64_t a_hi = umma_desc_sw128(sta + t * 128, p.desc_noboff ? 0u : (uint32_t)t);
-            const uint64_t a_lo = umma_desc_sw128(sta + kAPlaneBytes + t * 128, p.desc_noboff ? 0u : (uint32_t)t);
+            // tap t of the row: the same tile entered t pixel rows (128 B each) further.  The swizzle is a function of the
+            // absolute shared-memory address (TMA wrote it that way, UMMA reads it that way), so the descriptor only moves its
+            // start address; the "matrix base offset" field stays 0 -- measured: with base offset = t the 3x3 parity test
+            // fails (err 5.7 at scale 7), with 0 all 38 conv / update / encoder parity tests pass (profiles/r02_notes.md).
+            const uint64_t a_hi = umma_desc_sw128(sta + t * 128);
+            const uint64_t a_lo = umma_desc_sw128(sta + kAPlaneBytes + t * 128);
             const uint64_t b_all = umma_desc_sw128(smem_u32(smem_b + sb * Cfg::kBTileBytes));  // [B_hi ; B_lo], 2N rows
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k) {
@@ -505,13 +507,10 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   // weight tiles overlap the tail of this one.  Same-box A/B after the issue-loop fixes: 190 -> 175 us per update step.
   static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
   cfg.numAttrs = pdl;
-  ConvParams q = p;
-  static const int noboff = getenv("RAFT_B200_DESC_NOBOFF") ? 1 : 0;  // diagnostics (see ConvParams::desc_noboff)
-  q.desc_noboff = noboff;
   if (p.dbg || p.stat_part)
-    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps[0], maps[1], maps[2], maps[3], q, g));
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps[0], maps[1], maps[2], maps[3], p, g));
   else
-    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps[0], maps[1], maps[2], maps[3], q, g));
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps[0], maps[1], maps[2], maps[3], p, g));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }

@@ -132,11 +132,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows are 128 B (64 fp16),
 // 8-row core groups 1024 B apart (SBO); the tile base must be 1024-byte aligned.  Advancing by one
 // UMMA_K (16 fp16 = 32 B) adds 2 to the 16-byte-granular start address.
-// base_off: "matrix base offset" (bits [49,52)) = (start address >> 7) & 7 when the start is not aligned to the 1024-byte
-// repeat of the swizzle pattern (a tile entered a few 128-byte rows in: the row-halo taps of conv_tc.cu); 0 otherwise.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t base_off = 0) {
+// The start address may sit a few 128-byte rows inside a tile (row-halo taps of conv_tc.cu): the "matrix base offset" field
+// (bits [49,52)) stays 0 -- the hardware swizzles on the absolute address, exactly like the TMA write did (measured).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
-  d |= (uint64_t)(base_off & 7u) << 49;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address        bits [0,14)
   d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major) [16,30)
   d |= (uint64_t)(1024 >> 4) << 32;             // SBO = 1024 B          bits [32,46)
