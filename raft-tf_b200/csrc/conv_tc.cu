@@ -41,23 +41,23 @@ constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 // to the 1024-byte repeat of the 128-byte swizzle, which is fine: see the MMA loop).  The activation traffic of 3x3 / 1x5 convs
 // drops 3x / 5x -- the N <= 96 tiles are bound by the ~58 B/clk an SM ingests through TMA, not by the tensor pipe
 // (profiles/r01_notes.md, r02_notes.md).  Weight tiles ([B_hi ; B_lo], one per tap) travel through a ring of their own.
-constexpr int kAPlaneBytes = 17 * 1024;  // >= (128 + 4) rows x 128 B, 1024-byte multiple (swizzle repeat)
-constexpr int kAStageBytes = 2 * kAPlaneBytes;
+// The same trick along y serves the kh x 1 convs (second GRU pass): pixel tile 8 rows x 16 columns, ONE box of
+// (8 + kh - 1) x 16 pixels per channel chunk, tap ky = the tile entered ky * 16 rows further (hy = kh).
+// Ring geometry is a launch parameter (TileGeom): plane bytes = box pixels x 128 B rounded to the 1024-byte swizzle repeat,
+// SA activation stages (2 planes each), SB weight stages, together <= 200 KB.
+constexpr int kMaxAStages = 3, kMaxBStages = 8;
+constexpr int kRingBudget = 200 * 1024;
 
 template <int BLOCK_N>
 struct TcCfg {
   static constexpr int kBTileBytes = 2 * BLOCK_N * 128;  // [B_hi ; B_lo]
-  static constexpr int kAStages = 3;
-  static constexpr int kBStagesMax = (200 * 1024 - kAStages * kAStageBytes) / kBTileBytes;
-  static constexpr int kBStages = kBStagesMax > 8 ? 8 : kBStagesMax;  // 128: 3   96: 4   64: 6   <= 32: 8
   static constexpr int kAccCols = 2 * BLOCK_N;  // hi*hi | cross terms
   // two accumulator buffers; tiles of >= 32 columns take all 512 columns: a CTA that owns a single tile (batch 1) parks
   // the fp32 operands of the gate epilogues behind its one live buffer (Stash, common.cuh) -- up to 3 x BLOCK_N columns
   static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : 512;
-  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBTileBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kRingBudget + 1024 /*align slack*/ + 256 /*barriers*/;  // upper bound of every launch
   static constexpr int kColsPerWarp = BLOCK_N >= 96 ? 32 : 16;
   static constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1 column groups of epilogue warps
-  static_assert(kBStages >= 3 && kSmemBytes <= 227 * 1024, "shared-memory budget");
 };
 
 // EXTRAS: phase timestamps (p.dbg) and fused instance-norm statistics (p.stat_part) -- a separate instantiation, so that
@@ -68,15 +68,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const ConvParams p, const TileGeom g) {
   using Cfg = TcCfg<BLOCK_N>;
-  constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
+  const int SA = g.sa, SB = g.sb;
+  const int kAPlaneBytes = g.a_plane_bytes, kAStageBytes = 2 * g.a_plane_bytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + SA * kAStageBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + SB * Cfg::kBTileBytes);
-  uint64_t* a_empty = a_full + SA;
-  uint64_t* b_full = a_empty + SA;
-  uint64_t* b_empty = b_full + SB;
-  uint64_t* tmem_full_bar = b_empty + SB;         // [2]
+  uint64_t* a_empty = a_full + kMaxAStages;
+  uint64_t* b_full = a_empty + kMaxAStages;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* tmem_full_bar = b_empty + kMaxBStages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -85,10 +86,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const bool wide = epilogue_wide_ok(p);
   if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   const int chunks = conv_chunks(p);
-  const int hx = g.hx;                 // taps that share one activation box (kw, or 1)
-  const int kxg = p.kw / hx;           // groups of taps per filter row
+  const int hx = g.hx, hy = g.hy;      // taps along x / y that share one activation box (kw / kh, or 1)
+  const int kxg = p.kw / hx, kyg = p.kh / hy;  // tap groups per filter row / column
+  const int box_w = (1 << g.bw_log2) + hx - 1, box_h = (1 << g.bh_log2) + hy - 1;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
-  const uint32_t a_bytes = 2u * 128u * (uint32_t)(((1 << g.bw_log2) + hx - 1) << g.bh_log2);  // both planes of one box
+  const uint32_t a_bytes = 2u * 128u * (uint32_t)(box_w * box_h);  // both planes of one box
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
@@ -136,39 +138,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tma_load_3d(&tmB_lo, &b_full[sb], st + Cfg::kBTileBytes / 2, kcol, n0, wb);
           if (++sb == SB) { sb = 0; phb ^= 1; }
         };
+        // K order: channel chunk, filter row ky, tap kx -- for every path and every batch size (a batched run equals the
+        // per-sample runs bit for bit).  With hy = kh the rows of a chunk share one box, with hx = kw the taps of a row do.
+        struct Tap {
+          int cki, gy, gx, ty, tx;
+        };
+        auto tap_next = [&](Tap& t) {
+          if (++t.tx == hx) { t.tx = 0;
+            if (++t.ty == hy) { t.ty = 0;
+              if (++t.gx == kxg) { t.gx = 0;
+                if (++t.gy == kyg) { t.gy = 0; ++t.cki; } } } }
+        };
         if (!waited) {
           // first tile of the kernel: weight tiles of the first ring stages (the ring is empty: no waits), then wait for the
           // predecessor kernel (not when the B operand is itself an activation produced by an earlier kernel: corr build)
           if (!p.w_per_batch) {
-            int cki = 0, ky = 0, kx = 0;
+            Tap t{0, 0, 0, 0, 0};
             const int total = chunks * p.kh * p.kw;
             for (; b_ahead < SB && b_ahead < total; ++b_ahead) {
-              load_b(cki, ky, kx);
-              if (++kx == p.kw) { kx = 0; if (++ky == p.kh) { ky = 0; ++cki; } }
+              load_b(t.cki, t.gy * hy + t.ty, t.gx * hx + t.tx);
+              tap_next(t);
             }
           }
           asm volatile("griddepcontrol.wait;" ::: "memory");
           if (dbg) dbg[2] = gtime_ns();
           waited = true;
         }
-        // K order: channel chunk, then filter row ky, then the taps kx of that row (every path and every batch size: a
-        // batched run equals the per-sample runs bit for bit)
         for (int cki = 0; cki < chunks; ++cki) {
           const int c0 = p.in_choff + conv_chunk(p, cki) * kChunkK;
-          for (int ky = 0; ky < p.kh; ++ky) {
+          for (int gy = 0; gy < kyg; ++gy) {
             for (int gx = 0; gx < kxg; ++gx) {
               mbar_wait(&a_empty[sa], pha ^ 1);
               mbar_arrive_expect_tx(&a_full[sa], a_bytes);
               uint8_t* st = smem + sa * kAStageBytes;
-              const int xs = x0 + gx * hx - pw;  // hx == kw: gx == 0, the box starts pw pixels left of the tile
-              tma_load_4d(&tmA_hi, &a_full[sa], st, c0, xs, y0 + ky - ph, b);
-              tma_load_4d(&tmA_lo, &a_full[sa], st + kAPlaneBytes, c0, xs, y0 + ky - ph, b);
+              const int xs = x0 + gx * hx - pw, ys = y0 + gy * hy - ph;  // the box starts pw / ph pixels before the tile
+              tma_load_4d(&tmA_hi, &a_full[sa], st, c0, xs, ys, b);
+              tma_load_4d(&tmA_lo, &a_full[sa], st + kAPlaneBytes, c0, xs, ys, b);
               if (++sa == SA) { sa = 0; pha ^= 1; }
-              for (int t = 0; t < hx; ++t) {
-                if (b_ahead > 0) { --b_ahead; continue; }  // already in flight (requested before the wait)
-                mbar_wait(&b_empty[sb], phb ^ 1);
-                load_b(cki, ky, gx * hx + t);
-              }
+              for (int jy = 0; jy < hy; ++jy)
+                for (int jx = 0; jx < hx; ++jx) {
+                  if (b_ahead > 0) { --b_ahead; continue; }  // already in flight (requested before the wait)
+                  mbar_wait(&b_empty[sb], phb ^ 1);
+                  load_b(cki, gy * hy + jy, gx * hx + jx);
+                }
             }
           }
         }
@@ -181,7 +193,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
       int sa = 0, sb = 0, li = 0;
       uint32_t pha = 0, phb = 0;
-      const int groups = chunks * p.kh * kxg;  // activation boxes per tile
+      const int groups = chunks * kyg * kxg;  // activation boxes per tile
+      const int taps = hx * hy;               // taps per box
       for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int ab = li & 1;
         mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
@@ -192,15 +205,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tc_fence_after();
           if (dbg && li == 0 && gi == 0) dbg[3] = gtime_ns();
           const uint32_t sta = smem_u32(smem + sa * kAStageBytes);
-          for (int t = 0; t < hx; ++t) {
+          for (int t = 0; t < taps; ++t) {
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
+            const int toff = (hy > 1 ? t * box_w : t) * 128;  // hy > 1: hx == 1, tap ky = box row ky;  else tap kx = pixel kx
             // tap t of the row: the same tile entered t pixel rows (128 B each) further.  The swizzle is a function of the
             // absolute shared-memory address (TMA wrote it that way, UMMA reads it that way), so the descriptor only moves its
             // start address; the "matrix base offset" field stays 0 -- measured: with base offset = t the 3x3 parity test
             // fails (err 5.7 at scale 7), with 0 all 38 conv / update / encoder parity tests pass (profiles/r02_notes.md).
-            const uint64_t a_hi = umma_desc_sw128(sta + t * 128);
-            const uint64_t a_lo = umma_desc_sw128(sta + kAPlaneBytes + t * 128);
+            const uint64_t a_hi = umma_desc_sw128(sta + toff);
+            const uint64_t a_lo = umma_desc_sw128(sta + kAPlaneBytes + toff);
             const uint64_t b_all = umma_desc_sw128(smem_u32(smem_b + sb * Cfg::kBTileBytes));  // [B_hi ; B_lo], 2N rows
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k) {
@@ -497,7 +511,7 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
   if (p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;  // leave SMs to a concurrent conv (update.cu)
   cfg.gridDim = dim3(g.total_tiles < units ? g.total_tiles : units);
   cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = (size_t)g.sa * 2 * g.a_plane_bytes + (size_t)g.sb * Cfg::kBTileBytes + 1024 + 256;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -565,12 +579,30 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
   TileGeom g = choose_geom(p.h, p.w);
+  // Halo boxes (see conv_tc_kernel): kw > 1 and single-row pixel tiles -> the kw taps of a filter row share one box (hx);
+  // kh x 1 filters -> 8 x 16 pixel tiles and one box of (8 + kh - 1) x 16 pixels per chunk (hy).  Same K order either way.
+  // RAFT_B200_NO_ROWHALO=1 / RAFT_B200_NO_COLHALO=1 (A/B knobs): one box per tap -> identical results.
+  static const bool no_halo = getenv("RAFT_B200_NO_ROWHALO") != nullptr, no_colhalo = getenv("RAFT_B200_NO_COLHALO") != nullptr;
+  g.hx = g.hy = 1;
+  if (!no_halo && g.bh_log2 == 0 && p.kw > 1 && p.kw <= 5) {
+    g.hx = p.kw;
+  } else if (!no_colhalo && p.kw == 1 && p.kh > 1 && p.kh <= 5 && p.h >= 8 && p.w >= 16 && !p.stat_part) {
+    g.bw_log2 = 4; g.bh_log2 = 3;
+    g.tiles_x = (p.w + 15) / 16; g.tiles_y = (p.h + 7) / 8;
+    g.hy = p.kh;
+  }
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
   const int bn = choose_block_n(p.cout, m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
-  // Row halo: with single-row pixel tiles the kw taps of a filter row share ONE activation box (see conv_tc_kernel).
-  // RAFT_B200_NO_ROWHALO=1 (A/B knob): one box per tap, same kernel, same K order -> identical results.
-  static const bool no_halo = getenv("RAFT_B200_NO_ROWHALO") != nullptr;
-  g.hx = (!no_halo && g.bh_log2 == 0 && p.kw > 1 && p.kw <= 5) ? p.kw : 1;
+  {  // ring geometry
+    const int box_px = ((1 << g.bw_log2) + g.hx - 1) * ((1 << g.bh_log2) + g.hy - 1);
+    g.a_plane_bytes = (box_px * 128 + 1023) / 1024 * 1024;
+    const int btile = 2 * bn * 128;
+    g.sa = kMaxAStages;
+    while (g.sa > 2 && (kRingBudget - g.sa * 2 * g.a_plane_bytes) / btile < 3) --g.sa;
+    g.sb = (kRingBudget - g.sa * 2 * g.a_plane_bytes) / btile;
+    if (g.sb > kMaxBStages) g.sb = kMaxBStages;
+    RB_REQUIRE(g.sb >= 2, RB_ERR_UNSUPPORTED, "conv_tc: shared-memory rings do not fit (box %d px, tile width %d)", box_px, bn);
+  }
 #ifdef RB_EXPERIMENTS
   if (!p.stat_part) {
     bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
@@ -582,7 +614,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   {
     uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
     uint64_t str[3] = {(uint64_t)p.in_stride * 2, (uint64_t)p.in_stride * 2 * p.w, (uint64_t)p.in_stride * 2 * p.w * p.h};
-    uint32_t box[4] = {(uint32_t)kChunkK, (1u << g.bw_log2) + (uint32_t)(g.hx - 1), 1u << g.bh_log2, 1};
+    uint32_t box[4] = {(uint32_t)kChunkK, (1u << g.bw_log2) + (uint32_t)(g.hx - 1), (1u << g.bh_log2) + (uint32_t)(g.hy - 1), 1};
     int rc;
     if ((rc = cached_tmap(&maps[0], p.in_hi, 4, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[1], p.in_lo, 4, dims, str, box))) return rc;

@@ -203,7 +203,9 @@ struct TileGeom {
   int n_tiles;           // cout tiles
   int m_tiles;           // B * tiles_x * tiles_y pixel tiles
   int total_tiles;       // work items: m_tiles * n_tiles
-  int hx;                // taps of a filter row that share one activation box (row halo, conv_tc.cu): kw or 1
+  int hx, hy;            // taps along x / y that share one activation box (halo boxes, conv_tc.cu): kw / kh, or 1
+  int a_plane_bytes;     // shared bytes of one plane (hi or lo) of an activation box, 1024-byte multiple
+  int sa, sb;            // ring depths: activation boxes (2 planes each), weight tiles
 };
 
 #ifdef RB_EXPERIMENTS
