@@ -26,6 +26,7 @@ using namespace tc;
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;               // fp16 elements per 128-byte swizzled row
+constexpr int kATileBytes = kTileM * 128;  // 16 KB
 constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 
 // PERSISTENT kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, so CTAs that
@@ -34,50 +35,37 @@ constexpr int kTcThreads = 576;            // 18 warps: TMA, MMA, 16 epilogue
 // and the smem ring / its mbarrier phases simply continue across tiles.  With one wave of tiles (the update block
 // at batch 1) this degenerates to one tile per CTA; with many tiles (batched runs, encoder layers, the 3025-tile
 // correlation GEMM) the epilogue disappears behind the next tile's MMA loop.
-// A operand: one pipeline stage holds the hi and lo planes of ONE activation box of (bw + hx - 1) x bh pixels x 64 channels.
-// When the pixel tile is a single image row (bh = 1: every grid at least 128 wide) the taps of one filter ROW are 1-pixel
-// shifts of the same row, so the box is fetched ONCE per (chunk, ky) with a halo of kw - 1 pixels (hx = kw) and tap kx is
-// the UMMA descriptor of the same shared-memory tile advanced by kx rows of 128 bytes (the start is then no longer aligned
-// to the 1024-byte repeat of the 128-byte swizzle, which is fine: see the MMA loop).  The activation traffic of 3x3 / 1x5 convs
-// drops 3x / 5x -- the N <= 96 tiles are bound by the ~58 B/clk an SM ingests through TMA, not by the tensor pipe
-// (profiles/r01_notes.md, r02_notes.md).  Weight tiles ([B_hi ; B_lo], one per tap) travel through a ring of their own.
-// The same trick along y serves the kh x 1 convs (second GRU pass): pixel tile 8 rows x 16 columns, ONE box of
-// (8 + kh - 1) x 16 pixels per channel chunk, tap ky = the tile entered ky * 16 rows further (hy = kh).
-// Ring geometry is a launch parameter (TileGeom): plane bytes = box pixels x 128 B rounded to the 1024-byte swizzle repeat,
-// SA activation stages (2 planes each), SB weight stages, together <= 200 KB.
-constexpr int kMaxAStages = 3, kMaxBStages = 8;
-constexpr int kRingBudget = 200 * 1024;
-
 template <int BLOCK_N>
 struct TcCfg {
-  static constexpr int kBTileBytes = 2 * BLOCK_N * 128;  // [B_hi ; B_lo]
+  static constexpr int kBTileBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
   static constexpr int kAccCols = 2 * BLOCK_N;  // hi*hi | cross terms
   // two accumulator buffers; tiles of >= 32 columns take all 512 columns: a CTA that owns a single tile (batch 1) parks
   // the fp32 operands of the gate epilogues behind its one live buffer (Stash, common.cuh) -- up to 3 x BLOCK_N columns
   static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : 512;
-  static constexpr int kSmemBytes = kRingBudget + 1024 /*align slack*/ + 256 /*barriers*/;  // upper bound of every launch
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kColsPerWarp = BLOCK_N >= 96 ? 32 : 16;
   static constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1 column groups of epilogue warps
 };
 
+
+// PAIR = true: CTAs are launched as clusters of two that work on two pixel tiles of the SAME cout tile; CTA 0 fetches
+// B_hi, CTA 1 fetches B_lo, each with TMA multicast into both CTAs' shared memory, so every SM issues only half of
+// the weight-tile requests (the measured bound of the MMA loop is the ~38 B/clk a single SM can request from L2).
 // EXTRAS: phase timestamps (p.dbg) and fused instance-norm statistics (p.stat_part) -- a separate instantiation, so that
 // the kernel the update block runs stays below the 96-register cap of a 576-thread CTA without spills.
-template <int BLOCK_N, bool EXTRAS>
+template <int BLOCK_N, bool PAIR, bool EXTRAS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const ConvParams p, const TileGeom g) {
+               const ConvParams p, const TileGeom g, const int STAGES) {
   using Cfg = TcCfg<BLOCK_N>;
-  const int SA = g.sa, SB = g.sb;
-  const int kAPlaneBytes = g.a_plane_bytes, kAStageBytes = 2 * g.a_plane_bytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem + SA * kAStageBytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + SB * Cfg::kBTileBytes);
-  uint64_t* a_empty = a_full + kMaxAStages;
-  uint64_t* b_full = a_empty + kMaxAStages;
-  uint64_t* b_empty = b_full + kMaxBStages;
-  uint64_t* tmem_full_bar = b_empty + kMaxBStages;  // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -86,16 +74,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const bool wide = epilogue_wide_ok(p);
   if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
   const int chunks = conv_chunks(p);
-  const int hx = g.hx, hy = g.hy;      // taps along x / y that share one activation box (kw / kh, or 1)
-  const int kxg = p.kw / hx, kyg = p.kh / hy;  // tap groups per filter row / column
-  const int box_w = (1 << g.bw_log2) + hx - 1, box_h = (1 << g.bh_log2) + hy - 1;
+  const int taps = p.kh * p.kw;
+  const int kiters = taps * chunks;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
-  const uint32_t a_bytes = 2u * 128u * (uint32_t)(box_w * box_h);  // both planes of one box
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
-    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], Cfg::kGroups * 4); }
     fence_barrier_init();
     fence_proxy_async();
@@ -103,12 +88,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything of ours can reach them
   tc_fence_after();
   // warp-wide OR of identical values: lands in a UNIFORM register, so that ptxas does not wrap every tcgen05.mma of the
   // single issuing lane in an elect / R2UR.BROADCAST "waterfall" loop (that was ~50 cycles per MMA, 8 MMAs per k-iteration)
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
-  const int first = (int)blockIdx.x;      // first work item of this CTA
-  const int stride = (int)gridDim.x;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
+  const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // Programmatic dependent launch: this kernel may have been started while its predecessor is still running.  Everything
@@ -119,70 +106,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     if (elect_one()) {
       const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-      // ring slots and phases continue across tiles; no integer division in the loops below
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
-      int b_ahead = 0;  // weight tiles already requested before griddepcontrol.wait (first tile only)
+      int s = 0;          // ring slot and its phase; both continue across tiles.  No integer division in this loop:
+      uint32_t phase = 0;  // the k-iteration -> (chunk, kx, ky) mapping is advanced incrementally.
       bool waited = false;
       for (int tile = first; tile < g.total_tiles; tile += stride) {
-        const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+        const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
+        const int mt = PAIR ? 2 * mq + rank : mq;  // a trailing odd tile gets a dummy partner: b >= B, TMA zero-fills
         const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
         const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
         const int wb = p.w_per_batch ? min(b, p.B - 1) : 0;
-        auto load_b = [&](int cki, int ky, int kx) {
-          const int kcol = (ky * p.kw + kx) * p.cin_pad + conv_chunk(p, cki) * kChunkK;
-          uint8_t* st = smem_b + sb * Cfg::kBTileBytes;
-          mbar_arrive_expect_tx(&b_full[sb], Cfg::kBTileBytes);
-          tma_load_3d(&tmB_hi, &b_full[sb], st, kcol, n0, wb);
-          tma_load_3d(&tmB_lo, &b_full[sb], st + Cfg::kBTileBytes / 2, kcol, n0, wb);
-          if (++sb == SB) { sb = 0; phb ^= 1; }
+        // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
+        // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
+        // per-sample runs bit for bit.
+        struct KIter {
+          int cki, kx, ky, ck;
         };
-        // K order: channel chunk, filter row ky, tap kx -- for every path and every batch size (a batched run equals the
-        // per-sample runs bit for bit).  With hy = kh the rows of a chunk share one box, with hx = kw the taps of a row do.
-        struct Tap {
-          int cki, gy, gx, ty, tx;
+        auto k_next = [&](KIter& k) {
+          if (++k.ky == p.kh) {
+            k.ky = 0;
+            if (++k.kx == p.kw) { k.kx = 0; k.ck = conv_chunk(p, ++k.cki); }
+          }
         };
-        auto tap_next = [&](Tap& t) {
-          if (++t.tx == hx) { t.tx = 0;
-            if (++t.ty == hy) { t.ty = 0;
-              if (++t.gx == kxg) { t.gx = 0;
-                if (++t.gy == kyg) { t.gy = 0; ++t.cki; } } } }
+        auto load_a = [&](const KIter& k, int slot) {
+          uint8_t* st = smem + slot * Cfg::kStageBytes;
+          const int c0 = p.in_choff + k.ck * kChunkK;
+          tma_load_4d(&tmA_hi, &full_bar[slot], st, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
+          tma_load_4d(&tmA_lo, &full_bar[slot], st + kATileBytes, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
         };
+        auto load_b = [&](const KIter& k, int slot) {
+          uint8_t* st = smem + slot * Cfg::kStageBytes;
+          const int kcol = (k.ky * p.kw + k.kx) * p.cin_pad + k.ck * kChunkK;
+          if (PAIR) {  // half of the weight tile each, delivered to both CTAs
+            if (rank == 0) tma_load_3d_mc(&tmB_hi, &full_bar[slot], st + 2 * kATileBytes, kcol, n0, wb, (uint16_t)3);
+            else tma_load_3d_mc(&tmB_lo, &full_bar[slot], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb, (uint16_t)3);
+          } else {
+            tma_load_3d(&tmB_hi, &full_bar[slot], st + 2 * kATileBytes, kcol, n0, wb);
+            tma_load_3d(&tmB_lo, &full_bar[slot], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
+          }
+        };
+        KIter k = {0, 0, 0, conv_chunk(p, 0)};
+        int it0 = 0;
         if (!waited) {
-          // first tile of the kernel: weight tiles of the first ring stages (the ring is empty: no waits), then wait for the
-          // predecessor kernel (not when the B operand is itself an activation produced by an earlier kernel: corr build)
-          if (!p.w_per_batch) {
-            Tap t{0, 0, 0, 0, 0};
-            const int total = chunks * p.kh * p.kw;
-            for (; b_ahead < SB && b_ahead < total; ++b_ahead) {
-              load_b(t.cki, t.gy * hy + t.ty, t.gx * hx + t.tx);
-              tap_next(t);
-            }
+          // first tile of the kernel: weight tiles of the first ring stages, then wait for the predecessor kernel, then
+          // the activation tiles of the same stages (the ring is empty here: slots 0.., phase 0)
+          // (not when the B operand is itself an activation produced by an earlier kernel: corr build, w_per_batch)
+          const int pre = (PAIR || p.w_per_batch) ? 0 : (kiters < STAGES ? kiters : STAGES);
+          KIter kb = k;
+          for (int it = 0; it < pre; ++it) {
+            mbar_arrive_expect_tx(&full_bar[it], Cfg::kStageBytes);
+            load_b(kb, it);
+            k_next(kb);
           }
           asm volatile("griddepcontrol.wait;" ::: "memory");
           if (dbg) dbg[2] = gtime_ns();
+          for (int it = 0; it < pre; ++it) {
+            load_a(k, s);
+            k_next(k);
+            if (++s == STAGES) { s = 0; phase ^= 1; }
+          }
+          it0 = pre;
           waited = true;
         }
-        for (int cki = 0; cki < chunks; ++cki) {
-          const int c0 = p.in_choff + conv_chunk(p, cki) * kChunkK;
-          for (int gy = 0; gy < kyg; ++gy) {
-            for (int gx = 0; gx < kxg; ++gx) {
-              mbar_wait(&a_empty[sa], pha ^ 1);
-              mbar_arrive_expect_tx(&a_full[sa], a_bytes);
-              uint8_t* st = smem + sa * kAStageBytes;
-              const int xs = x0 + gx * hx - pw, ys = y0 + gy * hy - ph;  // the box starts pw / ph pixels before the tile
-              tma_load_4d(&tmA_hi, &a_full[sa], st, c0, xs, ys, b);
-              tma_load_4d(&tmA_lo, &a_full[sa], st + kAPlaneBytes, c0, xs, ys, b);
-              if (++sa == SA) { sa = 0; pha ^= 1; }
-              for (int jy = 0; jy < hy; ++jy)
-                for (int jx = 0; jx < hx; ++jx) {
-                  if (b_ahead > 0) { --b_ahead; continue; }  // already in flight (requested before the wait)
-                  mbar_wait(&b_empty[sb], phb ^ 1);
-                  load_b(cki, gy * hy + jy, gx * hx + jx);
-                }
-            }
-          }
+        for (int it = it0; it < kiters; ++it) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          load_a(k, s);
+          load_b(k, s);
+          k_next(k);
+          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
     }
@@ -191,42 +183,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (elect_one()) {
       constexpr uint32_t idesc_2n = umma_idesc_f16(2 * BLOCK_N);
       constexpr uint32_t idesc_n = umma_idesc_f16(BLOCK_N);
-      int sa = 0, sb = 0, li = 0;
-      uint32_t pha = 0, phb = 0;
-      const int groups = chunks * kyg * kxg;  // activation boxes per tile
-      const int taps = hx * hy;               // taps per box
+      int s = 0, li = 0;
+      uint32_t phase = 0;
       for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int ab = li & 1;
         mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + ab * Cfg::kAccCols;
-        for (int gi = 0; gi < groups; ++gi) {
-          mbar_wait(&a_full[sa], pha);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[s], phase);
           tc_fence_after();
-          if (dbg && li == 0 && gi == 0) dbg[3] = gtime_ns();
-          const uint32_t sta = smem_u32(smem + sa * kAStageBytes);
-          for (int t = 0; t < taps; ++t) {
-            mbar_wait(&b_full[sb], phb);
-            tc_fence_after();
-            const int toff = (hy > 1 ? t * box_w : t) * 128;  // hy > 1: hx == 1, tap ky = box row ky;  else tap kx = pixel kx
-            // tap t of the row: the same tile entered t pixel rows (128 B each) further.  The swizzle is a function of the
-            // absolute shared-memory address (TMA wrote it that way, UMMA reads it that way), so the descriptor only moves its
-            // start address; the "matrix base offset" field stays 0 -- measured: with base offset = t the 3x3 parity test
-            // fails (err 5.7 at scale 7), with 0 all 38 conv / update / encoder parity tests pass (profiles/r02_notes.md).
-            const uint64_t a_hi = umma_desc_sw128(sta + toff);
-            const uint64_t a_lo = umma_desc_sw128(sta + kAPlaneBytes + toff);
-            const uint64_t b_all = umma_desc_sw128(smem_u32(smem_b + sb * Cfg::kBTileBytes));  // [B_hi ; B_lo], 2N rows
+          if (dbg && li == 0 && it == 0) dbg[3] = gtime_ns();
+          const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t a_hi = umma_desc_sw128(st);
+          const uint64_t a_lo = umma_desc_sw128(st + kATileBytes);
+          const uint64_t b_all = umma_desc_sw128(st + 2 * kATileBytes);  // [B_hi ; B_lo], 2N rows
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) {
-              const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per k-slice, in 16-byte units
-              umma_f16(acc, a_hi + koff, b_all + koff, idesc_2n, (gi | t | k) != 0);
-              umma_f16(acc + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
-            }
-            umma_commit(&b_empty[sb]);  // frees the weight stage when these MMAs retire
-            if (++sb == SB) { sb = 0; phb ^= 1; }
+          for (int k = 0; k < kChunkK / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per k-slice, in 16-byte units
+            umma_f16(acc, a_hi + koff, b_all + koff, idesc_2n, (it | k) != 0);
+            umma_f16(acc + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
           }
-          umma_commit(&a_empty[sa]);    // ... and the activation stage after the last tap that reads it
-          if (++sa == SA) { sa = 0; pha ^= 1; }
+          if (PAIR) umma_commit_mc(&empty_bar[s], (uint16_t)3);  // both producers write into this stage of both CTAs
+          else umma_commit(&empty_bar[s]);                      // frees the smem stage when these MMAs retire
+          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[ab]);
         if (dbg && li == 0) dbg[4] = gtime_ns();
@@ -285,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       for (int tile = first; tile < g.total_tiles; tile += stride, ++li) {
         const int mq = tile / g.n_tiles, nt = tile - mq * g.n_tiles;
-        const int mt = mq;
+        const int mt = PAIR ? 2 * mq + rank : mq;
         const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
         const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
@@ -346,6 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (dbg && warp == 2 && lane == 0) dbg[6] = gtime_ns();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (dbg && threadIdx.x == 0) dbg[7] = gtime_ns();
   if (warp == 1) {
     tc_fence_after();
@@ -490,41 +471,48 @@ static int choose_block_n(int cout, long m_tiles, int ctas = 148) {  // ctas: pe
   return best;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = TcCfg<BLOCK_N>;
   static PerDeviceOnce attr_set;
   int dev = 0, rc_dev;
   if ((rc_dev = current_device(&dev))) return rc_dev;
   if (!attr_set.test(dev)) {
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RB_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set.set(dev);
   }
   const int num_sms = device_sm_count(dev);
   g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
   g.m_tiles = p.B * g.tiles_x * g.tiles_y;
-  g.total_tiles = g.m_tiles * g.n_tiles;
+  g.total_tiles = (PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  int units = num_sms;  // persistent: at most one CTA per SM
-  if (p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;  // leave SMs to a concurrent conv (update.cu)
-  cfg.gridDim = dim3(g.total_tiles < units ? g.total_tiles : units);
+  int units = PAIR ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
+  if (!PAIR && p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;  // leave SMs to a concurrent conv (update.cu)
+  cfg.gridDim = dim3((g.total_tiles < units ? g.total_tiles : units) * (PAIR ? 2 : 1));
   cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = (size_t)g.sa * 2 * g.a_plane_bytes + (size_t)g.sb * Cfg::kBTileBytes + 1024 + 256;
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   // Programmatic dependent launch (RAFT_B200_NO_PDL=1 turns it off): the dependent conv's prologue and its first
   // weight tiles overlap the tail of this one.  Same-box A/B after the issue-loop fixes: 190 -> 175 us per update step.
   static const int pdl = getenv("RAFT_B200_NO_PDL") ? 0 : 1;
-  cfg.numAttrs = pdl;
+  cfg.numAttrs = 1 + pdl;
+  int stages = Cfg::kStages;
+  static const int env_stages = getenv("RAFT_B200_TC_STAGES") ? atoi(getenv("RAFT_B200_TC_STAGES")) : 0;  // tuning knob
+  if (env_stages > 0 && env_stages < stages) stages = env_stages;
   if (p.dbg || p.stat_part)
-    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, true>, maps[0], maps[1], maps[2], maps[3], p, g));
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, PAIR, true>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
   else
-    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, false>, maps[0], maps[1], maps[2], maps[3], p, g));
+    RB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, PAIR, false>, maps[0], maps[1], maps[2], maps[3], p, g, stages));
   RB_CHECK_LAUNCH("conv_tc_kernel");
   return RB_OK;
 }
@@ -578,31 +566,9 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
 #endif
   RB_REQUIRE(p.cin_pad % kChunkK == 0 && p.in_stride % 8 == 0 && p.in_choff % 8 == 0, RB_ERR_BAD_SHAPE,
              "conv_tc: channel padding (cin_pad=%d stride=%d off=%d)", p.cin_pad, p.in_stride, p.in_choff);
-  TileGeom g = choose_geom(p.h, p.w);
-  // Halo boxes (see conv_tc_kernel): kw > 1 and single-row pixel tiles -> the kw taps of a filter row share one box (hx);
-  // kh x 1 filters -> 8 x 16 pixel tiles and one box of (8 + kh - 1) x 16 pixels per chunk (hy).  Same K order either way.
-  // RAFT_B200_NO_ROWHALO=1 / RAFT_B200_NO_COLHALO=1 (A/B knobs): one box per tap -> identical results.
-  static const bool no_halo = getenv("RAFT_B200_NO_ROWHALO") != nullptr, no_colhalo = getenv("RAFT_B200_NO_COLHALO") != nullptr;
-  g.hx = g.hy = 1;
-  if (!no_halo && g.bh_log2 == 0 && p.kw > 1 && p.kw <= 5) {
-    g.hx = p.kw;
-  } else if (!no_colhalo && p.kw == 1 && p.kh > 1 && p.kh <= 5 && p.h >= 8 && p.w >= 16 && !p.stat_part) {
-    g.bw_log2 = 4; g.bh_log2 = 3;
-    g.tiles_x = (p.w + 15) / 16; g.tiles_y = (p.h + 7) / 8;
-    g.hy = p.kh;
-  }
+  const TileGeom g = choose_geom(p.h, p.w);
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
   const int bn = choose_block_n(p.cout, m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
-  {  // ring geometry
-    const int box_px = ((1 << g.bw_log2) + g.hx - 1) * ((1 << g.bh_log2) + g.hy - 1);
-    g.a_plane_bytes = (box_px * 128 + 1023) / 1024 * 1024;
-    const int btile = 2 * bn * 128;
-    g.sa = kMaxAStages;
-    while (g.sa > 2 && (kRingBudget - g.sa * 2 * g.a_plane_bytes) / btile < 3) --g.sa;
-    g.sb = (kRingBudget - g.sa * 2 * g.a_plane_bytes) / btile;
-    if (g.sb > kMaxBStages) g.sb = kMaxBStages;
-    RB_REQUIRE(g.sb >= 2, RB_ERR_UNSUPPORTED, "conv_tc: shared-memory rings do not fit (box %d px, tile width %d)", box_px, bn);
-  }
 #ifdef RB_EXPERIMENTS
   if (!p.stat_part) {
     bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
@@ -614,7 +580,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   {
     uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
     uint64_t str[3] = {(uint64_t)p.in_stride * 2, (uint64_t)p.in_stride * 2 * p.w, (uint64_t)p.in_stride * 2 * p.w * p.h};
-    uint32_t box[4] = {(uint32_t)kChunkK, (1u << g.bw_log2) + (uint32_t)(g.hx - 1), (1u << g.bh_log2) + (uint32_t)(g.hy - 1), 1};
+    uint32_t box[4] = {(uint32_t)kChunkK, 1u << g.bw_log2, 1u << g.bh_log2, 1};
     int rc;
     if ((rc = cached_tmap(&maps[0], p.in_hi, 4, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[1], p.in_lo, 4, dims, str, box))) return rc;
@@ -628,12 +594,24 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
     if ((rc = cached_tmap(&maps[2], p.w_hi, 3, dims, str, box))) return rc;
     if ((rc = cached_tmap(&maps[3], p.w_lo, 3, dims, str, box))) return rc;
   }
+#ifdef RB_EXPERIMENTS
+  static const bool pair = getenv("RAFT_B200_PAIR") != nullptr;  // experiment: cluster-of-2 weight multicast
+  if (pair && m_tiles >= 2) {
+    switch (bn) {
+      case 16: return launch_cfg<16, true>(p, g, maps, s);
+      case 32: return launch_cfg<32, true>(p, g, maps, s);
+      case 64: return launch_cfg<64, true>(p, g, maps, s);
+      case 96: return launch_cfg<96, true>(p, g, maps, s);
+      default: return launch_cfg<128, true>(p, g, maps, s);
+    }
+  }
+#endif
   switch (bn) {
-    case 16: return launch_cfg<16>(p, g, maps, s);
-    case 32: return launch_cfg<32>(p, g, maps, s);
-    case 64: return launch_cfg<64>(p, g, maps, s);
-    case 96: return launch_cfg<96>(p, g, maps, s);
-    default: return launch_cfg<128>(p, g, maps, s);
+    case 16: return launch_cfg<16, false>(p, g, maps, s);
+    case 32: return launch_cfg<32, false>(p, g, maps, s);
+    case 64: return launch_cfg<64, false>(p, g, maps, s);
+    case 96: return launch_cfg<96, false>(p, g, maps, s);
+    default: return launch_cfg<128, false>(p, g, maps, s);
   }
 }
 

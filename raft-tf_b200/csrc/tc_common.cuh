@@ -132,8 +132,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows are 128 B (64 fp16),
 // 8-row core groups 1024 B apart (SBO); the tile base must be 1024-byte aligned.  Advancing by one
 // UMMA_K (16 fp16 = 32 B) adds 2 to the 16-byte-granular start address.
-// The start address may sit a few 128-byte rows inside a tile (row-halo taps of conv_tc.cu): the "matrix base offset" field
-// (bits [49,52)) stays 0 -- the hardware swizzles on the absolute address, exactly like the TMA write did (measured).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address        bits [0,14)
@@ -202,10 +200,7 @@ struct TileGeom {
   int tiles_x, tiles_y;  // per image
   int n_tiles;           // cout tiles
   int m_tiles;           // B * tiles_x * tiles_y pixel tiles
-  int total_tiles;       // work items: m_tiles * n_tiles
-  int hx, hy;            // taps along x / y that share one activation box (halo boxes, conv_tc.cu): kw / kh, or 1
-  int a_plane_bytes;     // shared bytes of one plane (hi or lo) of an activation box, 1024-byte multiple
-  int sa, sb;            // ring depths: activation boxes (2 planes each), weight tiles
+  int total_tiles;       // work items: m_tiles * n_tiles, or ceil(m_tiles/2) * n_tiles PAIRS in cluster mode
 };
 
 #ifdef RB_EXPERIMENTS
