@@ -94,6 +94,16 @@ struct ConvParams {
   const __half* in_lo;
   int in_stride, in_choff;
   int cin_pad;  // channels per tap in the packed weights (multiple of 64)
+  // Input VIEW (all 0 = the stride-1 'same' conv over a [B][h][w][in_stride] tensor).  The encoders use it for
+  //  * strided convs: output pixel (oy, ox), tap (ky, kx) reads input (oy*sy + ky - pad_y, ox*sx + kx - pad_x) of an
+  //    in_h x in_w input (TF SAME: pad before = total/2), out of range = 0 -- TMA element strides, no gather pass;
+  //  * the 7x7 stride-2 stem as a 4x1 conv over a space-to-depth image whose view pixel spans in_cext = 64 channels =
+  //    4 neighbouring physical pixels of in_stride = 16 channels (overlapping windows, encoder.cu).
+  int in_w, in_h;       // spatial extent of the view (0: w, h)
+  int in_rowpitch;      // elements between view rows (0: in_stride * in_w); images are in_rowpitch * in_h apart
+  int in_cext;          // channels addressable from one view pixel (0: in_stride)
+  int sx, sy;           // conv stride (0: 1)
+  int pad_explicit, pad_x, pad_y;  // pad before, when not the symmetric (k-1)/2
   // K sub-range: only the 64-channel chunks i in [0, ck_count) are multiplied, chunk i -> channel chunk
   // ck(i) = ck_begin + i + (i >= ck_skip_at ? ck_skip : 0).  ck_count == 0 means "all chunks".
   // (The iteration-invariant `inp` slice of the GRU inputs is convolved once per pair and skipped afterwards.)
@@ -104,6 +114,8 @@ struct ConvParams {
   double* stat_part;  // EPI_F32 + tensor-core wide epilogue: per-(sample, strip, channel) sum / sum of squares of the
   int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
   int stash;      // 1: single-tile CTAs park the gate epilogues' fp32 operands in spare TMEM columns during the MMA loop
+  int split_k;    // 1: K summed as (first half of the chunks) + (second half) (conv_tc.cu; cout <= 2, EPI_DELTA) ...
+  int split_cluster;  // ... set by the launcher: the halves run on the two CTAs of a cluster (one wave of pairs, batch 1)
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue
   long long* dbg;       // optional phase timestamps (globaltimer ns), 8 slots per CTA; see tools/phase_times.py
@@ -127,7 +139,22 @@ struct ConvParams {
   float* f0;
   float* f1;
   float* f2;
+  // EPI_ACT: optional residual (split planes, res_stride channels per pixel): y = relu(res + act(acc + bias)), the block
+  // output of ResidualBlock / BottleneckBlock (model_utils.py:31-35, 52-57)
+  const __half* res_hi;
+  const __half* res_lo;
+  int res_stride;
 };
+__host__ __device__ inline int conv_sx(const ConvParams& p) { return p.sx > 0 ? p.sx : 1; }
+__host__ __device__ inline int conv_sy(const ConvParams& p) { return p.sy > 0 ? p.sy : 1; }
+__host__ __device__ inline int conv_pad_x(const ConvParams& p) { return p.pad_explicit ? p.pad_x : (p.kw - 1) / 2; }
+__host__ __device__ inline int conv_pad_y(const ConvParams& p) { return p.pad_explicit ? p.pad_y : (p.kh - 1) / 2; }
+__host__ __device__ inline int conv_in_w(const ConvParams& p) { return p.in_w > 0 ? p.in_w : p.w; }
+__host__ __device__ inline int conv_in_h(const ConvParams& p) { return p.in_h > 0 ? p.in_h : p.h; }
+__host__ __device__ inline int conv_rowpitch(const ConvParams& p) { return p.in_rowpitch > 0 ? p.in_rowpitch : p.in_stride * conv_in_w(p); }
+__host__ __device__ inline bool conv_default_view(const ConvParams& p) {
+  return p.in_w == 0 && p.in_h == 0 && p.in_rowpitch == 0 && p.in_cext == 0 && p.sx <= 1 && p.sy <= 1 && !p.pad_explicit;
+}
 
 // Gate non-linearities on the SFU: exp via ex2.approx (abs. error of the gate < 3e-7 for |x| < 16, i.e.
 // below the 2^-22 operand truncation of the split GEMM that feeds them), reciprocal via rcp.approx.
@@ -175,6 +202,7 @@ __device__ __forceinline__ bool epilogue_wide_ok(const ConvParams& p) {
             al(p.f0) && al(p.f1);
   if (p.epi == EPI_ACT) {
     ok = ok && ((p.d0_stride | p.d0_choff) & 15) == 0;
+    if (p.res_hi) ok = ok && al(p.res_hi) && al(p.res_lo) && (p.res_stride & 15) == 0;
     if (p.d1_hi) ok = ok && ((p.d1_stride | p.d1_choff) & 15) == 0;
   } else if (p.epi == EPI_ZR || p.epi == EPI_Q) {
     ok = ok && ((p.d0_stride | p.d0_choff) & 15) == 0 && (p.hidden & 15) == 0;
@@ -261,6 +289,11 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int pix, int
       if (p.act == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      if (p.res_hi) {
+        const size_t ro = (size_t)pix * p.res_stride + c;
+        for (int i = 0; i < NV; ++i)
+          if (c + i < p.cout) y[i] = fmaxf(join_f32(p.res_hi[ro + i], p.res_lo[ro + i]) + y[i], 0.f);
       }
       store_split(p.d0_hi, p.d0_lo, p.d0_stride, p.d0_choff, c, y);
       if (p.d1_hi) store_split(p.d1_hi, p.d1_lo, p.d1_stride, p.d1_choff, c, y);
@@ -427,6 +460,14 @@ __device__ __forceinline__ void epilogue_wide16(const ConvParams& p, int pix, in
       if (p.act == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+      }
+      if (p.res_hi) {  // block output: relu(x + y), x as split planes (16 channels = 32 bytes per plane)
+        __align__(32) __half rh[16], rl[16];
+        const size_t ro = (size_t)pix * p.res_stride + c;
+        ld256_nc(reinterpret_cast<const float*>(p.res_hi + ro), reinterpret_cast<float*>(rh));
+        ld256_nc(reinterpret_cast<const float*>(p.res_lo + ro), reinterpret_cast<float*>(rl));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = fmaxf(join_f32(rh[i], rl[i]) + y[i], 0.f);
       }
       if (p.flow_tail && c + 16 == p.cout) {
         // motion encoder: [126 conv channels | flow] (model_utils.py:119) -- the flow slot completes the 16-channel group,

@@ -1,7 +1,8 @@
 // CUDA-core (fp32 FMA) implicit-GEMM convolution over split fp16 operands.
 // Bring-up and cross-check back end (RB_MATH_SIMT): same buffers, packed weights and fused
 // epilogues as the tcgen05 kernel in conv_tc.cu, so either can run any conv of the update block.
-// Implements tensorpack Conv2D(stride 1, 'same') = zero padding (k-1)/2  (SURVEY A14).
+// Implements tensorpack Conv2D(stride 1, 'same') = zero padding (k-1)/2  (SURVEY A14), and the strided / windowed input
+// views of the encoders (ConvParams, common.cuh).
 #include "common.cuh"
 
 namespace rb {
@@ -14,7 +15,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   const int pix0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int lr = tid / 4, lk = (tid % 4) * 4;  // loader: row (pixel / cout) and 4-channel group
-  const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+  const int ph = conv_pad_y(p), pw = conv_pad_x(p), csx = conv_sx(p), csy = conv_sy(p);
+  const int iw = conv_in_w(p), ih = conv_in_h(p), rowpitch = conv_rowpitch(p);  // input view (common.cuh)
   const int taps = p.kh * p.kw;
   // loader pixel coordinates
   const int lpix = pix0 + lr;
@@ -22,10 +24,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
   if (lpix < npix) { lx = lpix % p.w; ly = (lpix / p.w) % p.h; lb = lpix / (p.w * p.h); }
   float acc[4][4] = {};
   for (int t = 0; t < taps; ++t) {
-    const int dy = t / p.kw - ph, dx = t % p.kw - pw;
-    const int sy = ly + dy, sx = lx + dx;
-    const bool in_img = (lpix < npix) && sy >= 0 && sy < p.h && sx >= 0 && sx < p.w;
-    const size_t src = ((size_t)(lb * p.h + sy) * p.w + sx) * p.in_stride + p.in_choff;
+    const int sy = ly * csy + t / p.kw - ph, sx = lx * csx + t % p.kw - pw;
+    const bool in_img = (lpix < npix) && sy >= 0 && sy < ih && sx >= 0 && sx < iw;
+    const size_t src = ((size_t)lb * ih + sy) * rowpitch + (size_t)sx * p.in_stride + p.in_choff;
     const size_t wrow = ((size_t)(co0 + lr) * taps + t) * p.cin_pad;
     const bool w_ok = (co0 + lr) < p.cout_pad;
     for (int kk = 0; kk < conv_chunks(p) * 64; kk += 16) {

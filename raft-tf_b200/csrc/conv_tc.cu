@@ -43,8 +43,10 @@ struct TcCfg {
   static constexpr int kAccCols = 2 * BLOCK_N;  // hi*hi | cross terms
   // two accumulator buffers; tiles of >= 32 columns take all 512 columns: a CTA that owns a single tile (batch 1) parks
   // the fp32 operands of the gate epilogues behind its one live buffer (Stash, common.cuh) -- up to 3 x BLOCK_N columns
-  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // 16-wide tiles keep room for a second accumulator per buffer (K summed in two halves, see split_k below)
+  static constexpr int kBufCols = BLOCK_N == 16 ? 2 * kAccCols : kAccCols;
+  static constexpr int kTmemCols = BLOCK_N == 16 ? 128 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*split-K partials*/;
   static constexpr int kColsPerWarp = BLOCK_N >= 96 ? 32 : 16;
   static constexpr int kGroups = BLOCK_N / kColsPerWarp;  // 128:4  96:3  64:4  32:2  16:1 column groups of epilogue warps
 };
@@ -68,12 +70,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* red_bar = tmem_empty_bar + 3;  // split-K: the peer's partial sums have arrived (128 lane arrivals)
+  float2* red_buf = reinterpret_cast<float2*>(smem + STAGES * Cfg::kStageBytes + 256);  // [128 pixels] channels 0, 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = (EXTRAS && p.dbg) ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
   const bool wide = epilogue_wide_ok(p);
   if (dbg && threadIdx.x == 0) dbg[0] = gtime_ns();
-  const int chunks = conv_chunks(p);
+  // Split-K (p.split_k, 16-wide tiles with <= 2 real channels: the flow head's last conv, update.cu).  The sum over K is
+  // ALWAYS formed as (first half of the channel chunks) + (second half), each half in its own accumulator, so that the
+  // result does not depend on how it is executed:
+  //  * p.split_cluster = 1 (one wave of CTA pairs, batch 1): clusters of two CTAs share one pixel tile, CTA r multiplies
+  //    half r; CTA 1 hands its partial sums to CTA 0 through distributed shared memory, CTA 0 runs the epilogue on r0 + r1;
+  //  * else one CTA runs both halves back to back into two TMEM accumulators and its epilogue adds them the same way.
+  const bool halves = !PAIR && BLOCK_N == 16 && p.split_k;
+  const bool splitk = halves && p.split_cluster;
+  const int chunks = splitk ? conv_chunks(p) / 2 : conv_chunks(p);
   const int taps = p.kh * p.kw;
   const int kiters = taps * chunks;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
@@ -82,20 +94,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], Cfg::kGroups * 4); }
+    mbar_init(red_bar, 128);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything of ours can reach them
+  if (PAIR || splitk) cluster_sync_all();  // the peer's barriers must be initialised before anything of ours can reach them
   tc_fence_after();
   // warp-wide OR of identical values: lands in a UNIFORM register, so that ptxas does not wrap every tcgen05.mma of the
   // single issuing lane in an elect / R2UR.BROADCAST "waterfall" loop (that was ~50 cycles per MMA, 8 MMAs per k-iteration)
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
-  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
-  const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int krank = splitk ? (int)cluster_ctarank() : 0;
+  const int first = (PAIR || splitk) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
+  const int stride = (PAIR || splitk) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // Programmatic dependent launch: this kernel may have been started while its predecessor is still running.  Everything
@@ -105,7 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     if (elect_one()) {
-      const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+      const int ph = conv_pad_y(p), pw = conv_pad_x(p), csx = conv_sx(p), csy = conv_sy(p);
       int s = 0;          // ring slot and its phase; both continue across tiles.  No integer division in this loop:
       uint32_t phase = 0;  // the k-iteration -> (chunk, kx, ky) mapping is advanced incrementally.
       bool waited = false;
@@ -115,6 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int b = mt / tiles_per_img, trem = mt - b * tiles_per_img;
         const int ty = trem / g.tiles_x, tx = trem - ty * g.tiles_x;
         const int y0 = ty << g.bh_log2, x0 = tx << g.bw_log2, n0 = nt * BLOCK_N;
+        const int xs = x0 * csx - pw, ys = y0 * csy - ph;  // input coordinates of tap (0, 0) of the tile's first pixel
         const int wb = p.w_per_batch ? min(b, p.B - 1) : 0;
         // K order: channel chunk outermost, then kx, then ky -- the same order as conv_halo.cu, so that the two
         // kernels (chosen by tile count, i.e. by batch size) accumulate identically and a batched run equals the
@@ -131,8 +146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         auto load_a = [&](const KIter& k, int slot) {
           uint8_t* st = smem + slot * Cfg::kStageBytes;
           const int c0 = p.in_choff + k.ck * kChunkK;
-          tma_load_4d(&tmA_hi, &full_bar[slot], st, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
-          tma_load_4d(&tmA_lo, &full_bar[slot], st + kATileBytes, c0, x0 + k.kx - pw, y0 + k.ky - ph, b);
+          tma_load_4d(&tmA_hi, &full_bar[slot], st, c0, xs + k.kx, ys + k.ky, b);
+          tma_load_4d(&tmA_lo, &full_bar[slot], st + kATileBytes, c0, xs + k.kx, ys + k.ky, b);
         };
         auto load_b = [&](const KIter& k, int slot) {
           uint8_t* st = smem + slot * Cfg::kStageBytes;
@@ -145,7 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_3d(&tmB_lo, &full_bar[slot], st + 2 * kATileBytes + Cfg::kBTileBytes, kcol, n0, wb);
           }
         };
-        KIter k = {0, 0, 0, conv_chunk(p, 0)};
+        KIter k = {krank * chunks, 0, 0, conv_chunk(p, krank * chunks)};
         int it0 = 0;
         if (!waited) {
           // first tile of the kernel: weight tiles of the first ring stages, then wait for the predecessor kernel, then
@@ -189,8 +204,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ab = li & 1;
         mbar_wait(&tmem_empty_bar[ab], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t acc = tmem_base + ab * Cfg::kAccCols;
+        uint32_t acc = tmem_base + ab * Cfg::kBufCols;
+        const int it_half = (halves && !splitk) ? kiters / 2 : -1;  // first k-iteration of the second accumulator
         for (int it = 0; it < kiters; ++it) {
+          if constexpr (BLOCK_N == 16) {
+            if (it == it_half) acc += Cfg::kAccCols;
+          }
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
           if (dbg && li == 0 && it == 0) dbg[3] = gtime_ns();
@@ -201,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kChunkK / 16; ++k) {
             const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per k-slice, in 16-byte units
-            umma_f16(acc, a_hi + koff, b_all + koff, idesc_2n, (it | k) != 0);
+            umma_f16(acc, a_hi + koff, b_all + koff, idesc_2n, (BLOCK_N == 16 ? ((it != 0 && it != it_half) || k != 0) : (it | k) != 0));
             umma_f16(acc + BLOCK_N, a_lo + koff, b_all + koff, idesc_n, 1u);
           }
           if (PAIR) umma_commit_mc(&empty_bar[s], (uint16_t)3);  // both producers write into this stage of both CTAs
@@ -279,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
           if (dbg && warp == 2 && lane == 0) dbg[5] = gtime_ns();
         }
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ab * Cfg::kAccCols;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + ab * Cfg::kBufCols;
 #pragma unroll 1
         for (int cc = 0; cc < Cfg::kColsPerWarp; cc += 16) {
           const int c = grp * Cfg::kColsPerWarp + cc;
@@ -291,7 +310,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(d0[i]) + __uint_as_float(d1[i]) * kLoInv;
-          if (valid || stash_row != 0) {  // with a stash the TMEM reads inside are warp-collective: all lanes go
+          bool store = valid;
+          if constexpr (BLOCK_N == 16 && !PAIR) {
+            if (halves && !splitk) {  // second accumulator of the same CTA
+              tmem_ld16(trow + Cfg::kAccCols + c, d0);
+              tmem_ld16(trow + Cfg::kAccCols + BLOCK_N + c, d1);
+              tmem_ld_wait(d0, d1);
+              v[0] += __uint_as_float(d0[0]) + __uint_as_float(d1[0]) * kLoInv;
+              v[1] += __uint_as_float(d0[1]) + __uint_as_float(d1[1]) * kLoInv;
+            }
+            if (splitk) {
+              if (krank != 0) {  // partial sums of channels 0, 1 -> CTA 0 of the cluster; nothing else to do here
+                st_cluster_f32x2(mapa_u32(smem_u32(red_buf + r), 0), v[0], v[1]);
+                mbar_arrive_remote(mapa_u32(smem_u32(red_bar), 0));
+                store = false;
+              } else {
+                mbar_wait_cluster(red_bar, 0);
+                const float2 t = red_buf[r];
+                v[0] += t.x;
+                v[1] += t.y;
+              }
+            }
+          }
+          if (store || stash_row != 0) {  // with a stash the TMEM reads inside are warp-collective: all lanes go
             if (wide) {
               epilogue_wide16(p, pix, n0 + c, v, Stash{stash_row, BLOCK_N, c}, valid);
             } else {
@@ -355,13 +396,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int kind) {
+              const uint32_t* box, int kind, const uint32_t* elem_strides) {
   EncodeTiledFn fn = encode_fn();
   RB_REQUIRE(fn, RB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   const CUtensorMapDataType dt = kind == TMAP_F16_SW128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle sw = kind == TMAP_F16_SW128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -392,6 +433,7 @@ struct TmapKey {
   uint64_t d[4];
   uint64_t s[4];
   uint32_t b[4];
+  uint32_t e[4];
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -404,16 +446,18 @@ struct TmapKeyHash {
 };
 
 int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                const uint32_t* box, int kind) {
+                const uint32_t* box, int kind, const uint32_t* elem_strides) {
   static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey k;
   memset(&k, 0, sizeof(k));
   k.base = base;
   k.kind = (uint64_t)kind;
-  for (int i = 0; i < rank; ++i) { k.d[i] = dims[i]; k.s[i] = (i + 1 < rank) ? strides[i] : 0; k.b[i] = box[i]; }
+  for (int i = 0; i < rank; ++i) {
+    k.d[i] = dims[i]; k.s[i] = (i + 1 < rank) ? strides[i] : 0; k.b[i] = box[i]; k.e[i] = elem_strides ? elem_strides[i] : 1;
+  }
   auto it = cache.find(k);
   if (it != cache.end()) { *out = it->second; return RB_OK; }
-  int rc = make_tmap(out, base, rank, dims, strides, box, kind);
+  int rc = make_tmap(out, base, rank, dims, strides, box, kind, elem_strides);
   if (rc) return rc;
   if (cache.size() > 4096) cache.clear();
   cache.emplace(k, *out);
@@ -472,7 +516,7 @@ static int choose_block_n(int cout, long m_tiles, int ctas = 148) {  // ctas: pe
 }
 
 template <int BLOCK_N, bool PAIR>
-static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
+static int launch_cfg(const ConvParams& p_in, TileGeom g, const CUtensorMap* maps, cudaStream_t s) {
   using Cfg = TcCfg<BLOCK_N>;
   static PerDeviceOnce attr_set;
   int dev = 0, rc_dev;
@@ -483,20 +527,27 @@ static int launch_cfg(const ConvParams& p, TileGeom g, const CUtensorMap* maps, 
     attr_set.set(dev);
   }
   const int num_sms = device_sm_count(dev);
+  ConvParams p = p_in;
   g.n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
   g.m_tiles = p.B * g.tiles_x * g.tiles_y;
   g.total_tiles = (PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles;
+  // split-K: only when every pixel tile gets its own CTA pair in one wave (batch 1), else the plain persistent grid
+  if (p.split_k && !(BLOCK_N == 16 && !PAIR && p.cout <= 2 && p.epi == EPI_DELTA && !p.w_per_batch && conv_chunks(p) % 2 == 0))
+    p.split_k = 0;
+  static const bool no_cluster = getenv("RAFT_B200_NO_SPLITK_CLUSTER") != nullptr;  // test knob: same sums on one CTA
+  p.split_cluster = (p.split_k && 2 * g.total_tiles <= num_sms && p.cta_limit <= 0 && !no_cluster) ? 1 : 0;
+  const bool cluster2 = PAIR || p.split_cluster;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  int units = PAIR ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
-  if (!PAIR && p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;  // leave SMs to a concurrent conv (update.cu)
-  cfg.gridDim = dim3((g.total_tiles < units ? g.total_tiles : units) * (PAIR ? 2 : 1));
+  int units = cluster2 ? num_sms / 2 : num_sms;  // persistent: at most one CTA (pair) per SM (pair)
+  if (!cluster2 && p.cta_limit > 0 && p.cta_limit < units) units = p.cta_limit;  // leave SMs to a concurrent conv (update.cu)
+  cfg.gridDim = dim3((g.total_tiles < units ? g.total_tiles : units) * (cluster2 ? 2 : 1));
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.x = cluster2 ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -558,7 +609,7 @@ int conv_tc_prepare(const ConvParams& p, FusedJob* job) {
 
 int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
 #ifdef RB_EXPERIMENTS
-  if (p.kh * p.kw > 1 && !p.stat_part) {  // RAFT_B200_HALO=1: halo-tile kernel (each input pixel is fetched once per tap ROW)
+  if (p.kh * p.kw > 1 && !p.stat_part && conv_default_view(p)) {  // RAFT_B200_HALO=1: halo-tile kernel (each input pixel is fetched once per tap ROW)
     bool handled = false;
     int rc = launch_conv_halo(p, s, &handled);
     if (rc || handled) return rc;
@@ -570,7 +621,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   const long m_tiles = (long)p.B * g.tiles_x * g.tiles_y;
   const int bn = choose_block_n(p.cout, m_tiles, p.cta_limit > 0 && p.cta_limit < 148 ? p.cta_limit : 148);
 #ifdef RB_EXPERIMENTS
-  if (!p.stat_part) {
+  if (!p.stat_part && conv_default_view(p)) {
     bool handled = false;  // experimental cta_group::2 path (RAFT_B200_CTA2=1)
     int rc = launch_conv_tc2(p, s, bn, g.bw_log2, g.bh_log2, g.tiles_x, g.tiles_y, &handled);
     if (rc || handled) return rc;
@@ -578,12 +629,19 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
 #endif
   CUtensorMap maps[4];
   {
-    uint64_t dims[4] = {(uint64_t)p.in_stride, (uint64_t)p.w, (uint64_t)p.h, (uint64_t)p.B};
-    uint64_t str[3] = {(uint64_t)p.in_stride * 2, (uint64_t)p.in_stride * 2 * p.w, (uint64_t)p.in_stride * 2 * p.w * p.h};
-    uint32_t box[4] = {(uint32_t)kChunkK, 1u << g.bw_log2, 1u << g.bh_log2, 1};
+    // the input view (common.cuh): strided convs traverse it with TMA element strides -- a box of bw*sx x bh*sy input
+    // pixels delivers every sx-th / sy-th one, i.e. the bw x bh taps of the output tile
+    const int iw = conv_in_w(p), ih = conv_in_h(p), sx = conv_sx(p), sy = conv_sy(p);
+    const uint64_t rowpitch = (uint64_t)conv_rowpitch(p);
+    RB_REQUIRE(sx <= 2 && sy <= 2 && rowpitch % 8 == 0, RB_ERR_BAD_SHAPE, "conv_tc: stride (%d,%d) / row pitch %llu", sx, sy,
+               (unsigned long long)rowpitch);
+    uint64_t dims[4] = {(uint64_t)(p.in_cext > 0 ? p.in_cext : p.in_stride), (uint64_t)iw, (uint64_t)ih, (uint64_t)p.B};
+    uint64_t str[3] = {(uint64_t)p.in_stride * 2, rowpitch * 2, rowpitch * 2 * ih};
+    uint32_t box[4] = {(uint32_t)kChunkK, (1u << g.bw_log2) * sx, (1u << g.bh_log2) * sy, 1};
+    uint32_t es[4] = {1, (uint32_t)sx, (uint32_t)sy, 1};
     int rc;
-    if ((rc = cached_tmap(&maps[0], p.in_hi, 4, dims, str, box))) return rc;
-    if ((rc = cached_tmap(&maps[1], p.in_lo, 4, dims, str, box))) return rc;
+    if ((rc = cached_tmap(&maps[0], p.in_hi, 4, dims, str, box, tc::TMAP_F16_SW128, es))) return rc;
+    if ((rc = cached_tmap(&maps[1], p.in_lo, 4, dims, str, box, tc::TMAP_F16_SW128, es))) return rc;
   }
   {
     const uint64_t ktot = (uint64_t)p.kh * p.kw * p.cin_pad;
@@ -596,7 +654,7 @@ int launch_conv_tc(const ConvParams& p, cudaStream_t s) {
   }
 #ifdef RB_EXPERIMENTS
   static const bool pair = getenv("RAFT_B200_PAIR") != nullptr;  // experiment: cluster-of-2 weight multicast
-  if (pair && m_tiles >= 2) {
+  if (pair && m_tiles >= 2 && conv_default_view(p)) {
     switch (bn) {
       case 16: return launch_cfg<16, true>(p, g, maps, s);
       case 32: return launch_cfg<32, true>(p, g, maps, s);

@@ -5,15 +5,20 @@
 //
 // Activations are split fp16 tensors [pixel][Cpad] (Cpad = channels rounded up to 64, pad = 0).
 //   stride-1 convs  -> conv_tc implicit GEMM directly on the activation (TMA zero fill = TF SAME);
-//   strided convs   -> (7x7 s2 stem, 3x3 s2, 1x1 s2) a gather kernel lays the strided patches out as
-//                      [out pixel][kh*kw*cin] split rows with TF's asymmetric SAME offsets
-//                      (pad_before = total/2), then the conv is a 1x1 GEMM;
+//   strided convs   -> (3x3 s2, 1x1 s2) the same kernel over a strided input VIEW (ConvParams, common.cuh): TMA element
+//                      strides deliver every second pixel of the box, TF's asymmetric SAME offsets
+//                      (pad_before = total/2) are the tile's start coordinates -- no gather pass;
+//   7x7 s2 stem     -> one pass writes the 2x-1 image as a zero-padded space-to-depth tensor (2x2 pixels x 3 channels =
+//                      12 of 16 channels per cell); a 7x7 stride-2 window is 4x4 such cells, and the 4 cells of one
+//                      window row are 64 CONTIGUOUS channels, so the stem is a 4x1 conv (K = 4 x 64) over a view whose
+//                      pixels overlap (x pitch 16 channels, extent 64) -- 7 MB instead of the 86 MB im2col of round 1;
 //   instance norm   -> conv writes raw fp32, a two-stage deterministic reduction gives per-(sample,
 //                      channel) mean / biased variance, one pass applies (x-mean)*rstd (+ReLU, + the
 //                      residual add and final ReLU of the block) and re-splits;
 //   batch norm      -> folded into the conv weights/bias at pack time (inference statistics);
 //   none            -> bias + ReLU in the conv epilogue.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -70,7 +75,7 @@ static inline EncDesc enc_desc(int small) {
                : EncDesc{kBasicConvs, (int)(sizeof(kBasicConvs) / sizeof(EncConv))};
 }
 
-// packed form of one conv: strided convs become 1x1 GEMMs over the gathered K = k*k*cin
+// packed form of one conv: [cout_pad][kh*kw][cin_pad]; the stem as [cout_pad][4 cell rows][4 cells x 16]
 struct EncPacked {
   int kh, kw, cin_pad, cout, cout_pad;
   size_t hi, lo, bias;
@@ -83,9 +88,10 @@ static void enc_packed_layout(int small, int out_dim, std::vector<EncPacked>& P,
     const EncConv& c = d.convs[i];
     EncPacked& p = P[i];
     const int cout = c.cout < 0 ? out_dim : c.cout;
-    const bool gathered = c.stride != 1 || c.k == 7;
-    p.kh = p.kw = gathered ? 1 : c.k;
-    p.cin_pad = gathered ? pad64(c.k * c.k * c.cin) : pad64(c.cin);
+    const bool stem = c.k == 7;  // 4x1 conv over the space-to-depth view
+    p.kh = stem ? 4 : c.k;
+    p.kw = stem ? 1 : c.k;
+    p.cin_pad = stem ? 64 : pad64(c.cin);
     p.cout = cout;
     p.cout_pad = (cout + 15) / 16 * 16;
     size_t plane = (size_t)p.cout_pad * p.kh * p.kw * p.cin_pad * sizeof(__half);
@@ -97,87 +103,50 @@ static void enc_packed_layout(int small, int out_dim, std::vector<EncPacked>& P,
 }
 
 // ---- kernels ----------------------------------------------------------------------------------------
-// Strided patch gather: out[(b,oy,ox)][(ky*k+kx)*cin + ci] = in[b, oy*s+ky-pt, ox*s+kx-pl, ci] (0 outside).
-// IMG: the source is the fp32 [B,H,W,3] image in [0,1]; 2x-1 (RAFT.py:53-59) is applied on the fly.
-template <bool IMG>
-__global__ void enc_gather_kernel(const float* __restrict__ img, const __half* __restrict__ in_hi,
-                                  const __half* __restrict__ in_lo, int in_stride, __half* __restrict__ out_hi,
-                                  __half* __restrict__ out_lo, int B, int H, int W, int cin, int k, int s, int pt, int pl,
-                                  int oh, int ow, int kpad) {
-  const int K = k * k * cin;
+// Stem input: the 2x-1 image (RAFT.py:53-59) as a zero-padded space-to-depth tensor.  Padded image row r' = r + pt
+// (TF SAME: pt = total/2 rows of zeros before), cell (Y, X) holds rows 2Y, 2Y+1 and columns 2X, 2X+1: channel
+// (dy*2 + dx)*3 + c of 16 (12..15 = 0).  Output pixel (oy, ox) of the 7x7 stride-2 conv reads cells (oy..oy+3, ox..ox+3).
+// One thread per cell; WINDOWS = false: cells once, [B][Hp][Wp][16] (the conv's view overlaps them);
+// WINDOWS = true: every view pixel materialised, [B][Hp][Wo][4 cells x 16] (RAFT_B200_STEM_WINDOWS=1).
+template <bool WINDOWS>
+__global__ void enc_stem_s2d_kernel(const float* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B,
+                                    int H, int W, int pt, int pl, int Hp, int Wp, int Wo) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)B * oh * ow * kpad;
-  if (i >= total) return;
-  const int kk = i % kpad;
-  size_t px = i / kpad;
-  __half hi = __float2half_rn(0.f), lo = hi;
-  if (kk < K) {
-    const int ci = kk % cin, t = kk / cin, kx = t % k, ky = t / k;
-    const int ox = px % ow, oy = (px / ow) % oh, b = px / ((size_t)ow * oh);
-    const int iy = oy * s + ky - pt, ix = ox * s + kx - pl;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      size_t src = ((size_t)(b * H + iy) * W + ix);
-      if (IMG) {
-        split_f32(2.0f * img[src * cin + ci] - 1.0f, hi, lo);
-      } else {
-        hi = in_hi[src * in_stride + ci];
-        lo = in_lo[src * in_stride + ci];
+  if (i >= (size_t)B * Hp * Wp) return;
+  const int X = i % Wp, Y = (i / Wp) % Hp, b = i / ((size_t)Wp * Hp);
+  __align__(16) __half hi[16], lo[16];
+#pragma unroll
+  for (int j = 12; j < 16; ++j) hi[j] = lo[j] = __float2half_rn(0.f);
+  const float* base = img + (size_t)b * H * W * 3;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int r = 2 * Y + dy - pt, q = 2 * X + dx - pl;
+      const bool in = r >= 0 && r < H && q >= 0 && q < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int j = (dy * 2 + dx) * 3 + c;
+        if (in) split_f32(2.0f * __ldg(base + ((size_t)r * W + q) * 3 + c) - 1.0f, hi[j], lo[j]);
+        else hi[j] = lo[j] = __float2half_rn(0.f);  // SAME zero padding is applied AFTER the 2x-1 preprocessing
       }
     }
-  }
-  out_hi[i] = hi;
-  out_lo[i] = lo;
-}
-
-// Stem gather (7x7 stride 2 over the 3-channel image): 8 consecutive k per thread, 16-byte stores.  The (ky,kx,ci)
-// triple is advanced incrementally (r01 profile: the div/mod version was the largest single encoder kernel).
-__global__ void enc_gather_img8_kernel(const float* __restrict__ img, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                       int B, int H, int W, int cin, int k, int s, int pt, int pl, int oh, int ow, int kpad) {
-  const int K = k * k * cin, k8 = kpad / 8;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * oh * ow * k8) return;
-  const int kk0 = (i % k8) * 8;
-  size_t px = i / k8;
-  const int ox = px % ow, oy = (px / ow) % oh, b = px / ((size_t)ow * oh);
-  int ci = kk0 % cin, t = kk0 / cin, kx = t % k, ky = t / k;
-  const int iy0 = oy * s - pt, ix0 = ox * s - pl;
-  const float* base = img + (size_t)b * H * W * cin;
-  __align__(16) __half hi[8], lo[8];
+  const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lo);
+  if (!WINDOWS) {
+    const size_t o = (((size_t)b * Hp + Y) * Wp + X) * 16;
+    reinterpret_cast<uint4*>(out_hi + o)[0] = h4[0]; reinterpret_cast<uint4*>(out_hi + o)[1] = h4[1];
+    reinterpret_cast<uint4*>(out_lo + o)[0] = l4[0]; reinterpret_cast<uint4*>(out_lo + o)[1] = l4[1];
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int iy = iy0 + ky, ix = ix0 + kx;
-    const bool in = (kk0 + j < K) && iy >= 0 && iy < H && ix >= 0 && ix < W;
-    if (in) split_f32(2.0f * __ldg(base + ((size_t)iy * W + ix) * cin + ci) - 1.0f, hi[j], lo[j]);  // RAFT.py:53-59
-    else hi[j] = lo[j] = __float2half_rn(0.f);  // SAME zero padding is applied AFTER the 2x-1 preprocessing
-    if (++ci == cin) { ci = 0; if (++kx == k) { kx = 0; ++ky; } }
-  }
-  *reinterpret_cast<uint4*>(out_hi + px * kpad + kk0) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(out_lo + px * kpad + kk0) = *reinterpret_cast<const uint4*>(lo);
-}
-
-// Same gather for split sources whose channel count is a multiple of 8: one thread moves 8 channels
-// (16 bytes per plane) -- the 3x3/1x1 stride-2 convs of layer2/layer3.
-__global__ void enc_gather8_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_stride,
-                                   __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W, int cin,
-                                   int k, int s, int pt, int pl, int oh, int ow, int kpad) {
-  const int K = k * k * cin, k8 = kpad / 8;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * oh * ow * k8) return;
-  const int kk = (i % k8) * 8;
-  size_t px = i / k8;
-  uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-  if (kk < K) {
-    const int ci = kk % cin, t = kk / cin, kx = t % k, ky = t / k;
-    const int ox = px % ow, oy = (px / ow) % oh, b = px / ((size_t)ow * oh);
-    const int iy = oy * s + ky - pt, ix = ox * s + kx - pl;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      size_t src = ((size_t)(b * H + iy) * W + ix) * in_stride + ci;
-      hi = *reinterpret_cast<const uint4*>(in_hi + src);
-      lo = *reinterpret_cast<const uint4*>(in_lo + src);
+    for (int j = 0; j < 4; ++j) {  // cell X is cell j of the window that starts at X - j
+      const int xw = X - j;
+      if (xw < 0 || xw >= Wo) continue;
+      const size_t o = (((size_t)b * Hp + Y) * Wo + xw) * 64 + j * 16;
+      reinterpret_cast<uint4*>(out_hi + o)[0] = h4[0]; reinterpret_cast<uint4*>(out_hi + o)[1] = h4[1];
+      reinterpret_cast<uint4*>(out_lo + o)[0] = l4[0]; reinterpret_cast<uint4*>(out_lo + o)[1] = l4[1];
     }
   }
-  *reinterpret_cast<uint4*>(out_hi + px * kpad + kk) = hi;
-  *reinterpret_cast<uint4*>(out_lo + px * kpad + kk) = lo;
 }
 
 // instance-norm statistics, stage 1: per (sample, pixel strip) partial sum / sum of squares per channel
@@ -254,30 +223,10 @@ __global__ void inorm_apply_kernel(const float* __restrict__ x, const float2* __
   *reinterpret_cast<uint4*>(out_hi + px * out_stride + c) = *reinterpret_cast<const uint4*>(oh);
   *reinterpret_cast<uint4*>(out_lo + px * out_stride + c) = *reinterpret_cast<const uint4*>(ol);
 }
-// out = relu(a + b) on split tensors (block output for the folded-BN / no-norm encoders), 8 channels per thread
-__global__ void add_relu_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo, int a_stride,
-                                const __half* __restrict__ b_hi, const __half* __restrict__ b_lo, int b_stride,
-                                __half* __restrict__ o_hi, __half* __restrict__ o_lo, int o_stride, size_t npx, int C) {
-  const int c8 = C / 8;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npx * c8) return;
-  const int c = (i % c8) * 8;
-  const size_t px = i / c8;
-  __align__(16) __half ah[8], al_[8], bh[8], bl[8], oh[8], ol[8];
-  *reinterpret_cast<uint4*>(ah) = *reinterpret_cast<const uint4*>(a_hi + px * a_stride + c);
-  *reinterpret_cast<uint4*>(al_) = *reinterpret_cast<const uint4*>(a_lo + px * a_stride + c);
-  *reinterpret_cast<uint4*>(bh) = *reinterpret_cast<const uint4*>(b_hi + px * b_stride + c);
-  *reinterpret_cast<uint4*>(bl) = *reinterpret_cast<const uint4*>(b_lo + px * b_stride + c);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) split_f32(fmaxf(join_f32(ah[k], al_[k]) + join_f32(bh[k], bl[k]), 0.f), oh[k], ol[k]);
-  *reinterpret_cast<uint4*>(o_hi + px * o_stride + c) = *reinterpret_cast<const uint4*>(oh);
-  *reinterpret_cast<uint4*>(o_lo + px * o_stride + c) = *reinterpret_cast<const uint4*>(ol);
-}
-
 // ---- workspace -----------------------------------------------------------------------------------------
 struct EncWs {
   SplitPtr act[4];  // rotating activation buffers
-  SplitPtr col;     // gathered patches of strided convs
+  SplitPtr col;     // space-to-depth cells of the stem
   float* f32;       // raw conv output awaiting instance norm
   double* part;     // instance-norm partial sums [B][strips][2][C]
   size_t part_cap;  // strips * C it can hold per sample
@@ -298,7 +247,8 @@ static EncWs enc_ws_layout(int small, int B, int H, int W, void* base) {
     w.act[i].hi = reinterpret_cast<__half*>(b + off); off += act_plane;
     w.act[i].lo = reinterpret_cast<__half*>(b + off); off += act_plane;
   }
-  const size_t col_plane = al(px2 * pad64(147) * sizeof(__half));  // stem: K = 7*7*3 -> 192; others are smaller
+  // stem input cells: (Ho+3) x (Wo+3) x 16, or (Ho+3) x Wo x 64 with materialised windows
+  const size_t col_plane = al((size_t)B * ((H + 1) / 2 + 3) * ((W + 1) / 2 + 3) * 64 * sizeof(__half));
   w.col.hi = reinterpret_cast<__half*>(b + off); off += col_plane;
   w.col.lo = reinterpret_cast<__half*>(b + off); off += col_plane;
   w.f32 = reinterpret_cast<float*>(b + off); off += al(px2 * (size_t)(small ? 64 : 128) * sizeof(float));
@@ -334,34 +284,35 @@ static int enc_conv(const EncRun& R, int i, const float* img, SplitPtr in, int i
   const EncConv& c = enc_desc(R.small).convs[i];
   const EncPacked& pk = (*R.P)[i];
   int oh = h, ow = w;
-  SplitPtr src = in;
-  int src_stride = in_stride;
-  const bool gathered = c.stride != 1 || c.k == 7;
-  if (gathered) {
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.in_hi = in.hi; p.in_lo = in.lo; p.in_stride = in_stride; p.in_choff = 0; p.cin_pad = pk.cin_pad;
+  if (c.k == 7) {  // stem: 4x1 conv over the space-to-depth view of the image
     int pt, pl;
     same_pad(h, c.k, c.stride, &pt, &oh);
     same_pad(w, c.k, c.stride, &pl, &ow);
-    size_t total = (size_t)R.B * oh * ow * pk.cin_pad;
-    unsigned blocks = (unsigned)((total + 255) / 256);
-    if (img) {
-      size_t t8 = total / 8;
-      enc_gather_img8_kernel<<<(unsigned)((t8 + 255) / 256), 256, 0, R.s>>>(img, R.ws.col.hi, R.ws.col.lo, R.B, h, w, c.cin, c.k,
-                                                                          c.stride, pt, pl, oh, ow, pk.cin_pad);
-    }
-    else if (c.cin % 8 == 0) {
-      size_t t8 = total / 8;
-      enc_gather8_kernel<<<(unsigned)((t8 + 255) / 256), 256, 0, R.s>>>(in.hi, in.lo, in_stride, R.ws.col.hi, R.ws.col.lo, R.B, h, w,
-                                                                      c.cin, c.k, c.stride, pt, pl, oh, ow, pk.cin_pad);
-    } else
-      enc_gather_kernel<false><<<blocks, 256, 0, R.s>>>(nullptr, in.hi, in.lo, in_stride, R.ws.col.hi, R.ws.col.lo, R.B, h, w,
-                                                        c.cin, c.k, c.stride, pt, pl, oh, ow, pk.cin_pad);
-    RB_CHECK_LAUNCH("enc_gather_kernel");
-    src = R.ws.col;
-    src_stride = pk.cin_pad;
+    static const bool windows = getenv("RAFT_B200_STEM_WINDOWS") != nullptr;  // A/B knob: materialised windows
+    const int Hp = oh + 3, Wp = ow + 3;
+    const size_t cells = (size_t)R.B * Hp * Wp;
+    if (windows)
+      enc_stem_s2d_kernel<true><<<(unsigned)((cells + 255) / 256), 256, 0, R.s>>>(img, R.ws.col.hi, R.ws.col.lo, R.B, h, w, pt, pl, Hp, Wp, ow);
+    else
+      enc_stem_s2d_kernel<false><<<(unsigned)((cells + 255) / 256), 256, 0, R.s>>>(img, R.ws.col.hi, R.ws.col.lo, R.B, h, w, pt, pl, Hp, Wp, ow);
+    RB_CHECK_LAUNCH("enc_stem_s2d_kernel");
+    p.in_hi = R.ws.col.hi; p.in_lo = R.ws.col.lo;
+    p.in_stride = windows ? 64 : 16;
+    p.in_cext = 64;
+    p.in_w = ow; p.in_h = Hp;
+    p.in_rowpitch = windows ? ow * 64 : Wp * 16;
+    p.pad_explicit = 1; p.pad_x = 0; p.pad_y = 0;
+  } else if (c.stride != 1) {  // strided view of the activation, TF SAME offsets
+    int pt, pl;
+    same_pad(h, c.k, c.stride, &pt, &oh);
+    same_pad(w, c.k, c.stride, &pl, &ow);
+    p.in_w = w; p.in_h = h;
+    p.sx = p.sy = c.stride;
+    p.pad_explicit = 1; p.pad_x = pl; p.pad_y = pt;
   }
-  ConvParams p;
-  memset(&p, 0, sizeof(p));
-  p.in_hi = src.hi; p.in_lo = src.lo; p.in_stride = src_stride; p.in_choff = 0; p.cin_pad = pk.cin_pad;
   p.w_hi = reinterpret_cast<const __half*>(R.blob + pk.hi);
   p.w_lo = reinterpret_cast<const __half*>(R.blob + pk.lo);
   p.bias = reinterpret_cast<const float*>(R.blob + pk.bias);
@@ -401,14 +352,8 @@ static int enc_conv(const EncRun& R, int i, const float* img, SplitPtr in, int i
   } else {  // batch norm folded into W/b, or no norm: bias (+ReLU) in the epilogue
     p.epi = EPI_ACT; p.act = relu ? ACT_RELU : ACT_NONE;
     p.d0_hi = dst.hi; p.d0_lo = dst.lo; p.d0_stride = dst_stride; p.d0_choff = 0;
+    p.res_hi = res.hi; p.res_lo = res.lo; p.res_stride = res_stride;  // block output relu(x + y) in the same epilogue
     if ((rc = launch_conv(p, R.s))) return rc;
-    if (res.hi) {
-      size_t npx = (size_t)R.B * oh * ow;
-      size_t n = npx * (pk.cout / 8);
-      add_relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, R.s>>>(res.hi, res.lo, res_stride, dst.hi, dst.lo, dst_stride, dst.hi,
-                                                                    dst.lo, dst_stride, npx, pk.cout);
-      RB_CHECK_LAUNCH("add_relu_kernel");
-    }
   }
   *oh_ = oh;
   *ow_ = ow;
@@ -519,7 +464,7 @@ extern "C" int rb_encoder_weights_pack(int small, int norm, int out_dim, const f
     __half* lo = reinterpret_cast<__half*>(host.data() + p.lo);
     float* bias = reinterpret_cast<float*>(host.data() + p.bias);
     const int cout = p.cout, taps_ref = c.k * c.k;
-    const bool gathered = c.stride != 1 || c.k == 7;
+    const bool stem = c.k == 7;
     const bool fold = norm == NORM_BATCH && c.norm[0] != 0;
     RB_REQUIRE(!fold || (bn_host && bn_host[i]), RB_ERR_BAD_ARG, "rb_encoder_weights_pack: missing BN statistics for %s", c.norm);
     for (int co = 0; co < cout; ++co) {
@@ -532,8 +477,11 @@ extern "C" int rb_encoder_weights_pack(int small, int norm, int out_dim, const f
       for (int t = 0; t < taps_ref; ++t)
         for (int ci = 0; ci < c.cin; ++ci) {
           const float val = (float)(W_host[i][((size_t)t * c.cin + ci) * cout + co] * scale);
-          const size_t o = gathered ? ((size_t)co * p.cin_pad + (size_t)t * c.cin + ci)
-                                    : (((size_t)co * taps_ref + t) * p.cin_pad + ci);
+          size_t o = ((size_t)co * taps_ref + t) * p.cin_pad + ci;
+          if (stem) {  // tap (ky, kx) = cell (ky/2, kx/2), sub-pixel (ky%2, kx%2): [co][cell row][cell x 16 + sub*3 + ci]
+            const int ky = t / c.k, kx = t % c.k;
+            o = ((size_t)co * 4 + ky / 2) * 64 + (kx / 2) * 16 + ((ky & 1) * 2 + (kx & 1)) * 3 + ci;
+          }
           split_f32(val, hi[o], lo[o]);
         }
       bias[co] = (float)(b_host[i][co] * scale + shift);

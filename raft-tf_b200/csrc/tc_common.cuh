@@ -191,7 +191,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* a, uint32_t* b) {
 // up to 4 dims (innermost first), zero fill for out-of-bounds boxes; kind selects element type and swizzle
 enum { TMAP_F16_SW128 = 0, TMAP_F32_SW64 = 1, TMAP_F32_SW64_GATHER = 2 };  // GATHER: as SW64 but without L2 promotion (lookup v5)
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int kind);
+              const uint32_t* box, int kind, const uint32_t* elem_strides = nullptr);
 
 }  // namespace tc
 
@@ -230,7 +230,7 @@ int launch_fused_jobs(const FusedJobs& jobs, cudaStream_t s);
 
 // per-thread cache of encoded tensor maps (conv_tc.cu)
 int cached_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                const uint32_t* box, int kind = tc::TMAP_F16_SW128);
+                const uint32_t* box, int kind = tc::TMAP_F16_SW128, const uint32_t* elem_strides = nullptr);
 
 }  // namespace rb
 
@@ -242,6 +242,32 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// wait whose acquire covers writes a peer CTA made to this CTA's shared memory before its release.cluster arrive
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if ((++spins & 0xFFF) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        printf("raft_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");

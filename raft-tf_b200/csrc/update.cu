@@ -650,6 +650,11 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     if ((rc = launch_conv_dbg(p, s))) return rc;
     p = base_params(v, L, blob, P_FH2, W.fh, v.fh, 0, B, h, w);
     p.epi = EPI_DELTA; p.f1 = coords1; p.f2 = delta_out;
+    // 36 k-iterations on 55 CTAs at batch 1 while 93 SMs idle: two CTAs per pixel tile, half of the channel chunks each
+    // (conv_tc.cu, split-K over a cluster when the tiles fit one wave of CTA pairs; the same two-halves sum on one CTA
+    // otherwise, so batched and per-sample runs stay bit-identical).  RAFT_B200_NO_SPLITK=1: one accumulator.
+    static const bool no_splitk = getenv("RAFT_B200_NO_SPLITK") != nullptr;
+    p.split_k = no_splitk ? 0 : 1;
     // RAFT_B200_FH2_SIMT=1: CUDA-core kernel instead of the N=16 implicit GEMM (profiles/r01_notes.md) -> opt-in.
     static const bool fh2_simt = getenv("RAFT_B200_FH2_SIMT") != nullptr;
     const bool direct = !fused && fh2_simt && p.kh == 3 && p.kw == 3 && p.in_choff == 0 && p.in_stride % 8 == 0 &&

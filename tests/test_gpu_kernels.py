@@ -279,7 +279,9 @@ def test_error_paths_do_not_abort(cuda):
 @pytest.mark.parametrize("mode", ["tc", "simt"])
 @pytest.mark.parametrize("small,name,norm,out_dim,B,H,W", [
     (False, "fnet", "instance", 256, 2, 64, 96), (False, "cnet", "batch", 256, 1, 72, 104),
-    (True, "fnet", "instance", 128, 2, 64, 96), (True, "cnet", "none", 160, 1, 72, 104)])
+    (True, "fnet", "instance", 128, 2, 64, 96), (True, "cnet", "none", 160, 1, 72, 104),
+    # odd sizes at every level: TF SAME pads 3|3 (stem) and 1|1 (3x3 s2) instead of 2|3 and 0|1
+    (False, "cnet", "batch", 256, 2, 71, 99), (True, "fnet", "instance", 128, 1, 67, 85)])
 def test_encoder(cuda, mode, small, name, norm, out_dim, B, H, W):
     """BasicEncoder / SmallEncoder (model_utils.py:61-105) on raft_b200's own kernels vs the fp64 oracle:
     asymmetric TF 'SAME' padding on the stride-2 convs, instance norm / folded batch norm / no norm."""

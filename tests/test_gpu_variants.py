@@ -25,7 +25,8 @@ def _kernel_parity(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
 
 
-@pytest.mark.parametrize("knob", ["RAFT_B200_NO_HOIST", "RAFT_B200_NO_STASH", "RAFT_B200_FH2_SIMT", "RAFT_B200_NO_PDL"])
+@pytest.mark.parametrize("knob", ["RAFT_B200_NO_HOIST", "RAFT_B200_NO_STASH", "RAFT_B200_FH2_SIMT", "RAFT_B200_NO_PDL",
+                                  "RAFT_B200_STEM_WINDOWS"])
 def test_variant_passes_conv_and_update_parity(cuda, knob):
     _kernel_parity(dict(os.environ, **{knob: "1"}))
 
