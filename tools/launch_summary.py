@@ -5,8 +5,8 @@ hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 hdr = rows[hi]; kn = hdr.index('Kernel Name'); mv = hdr.index('Metric Value'); gs = hdr.index('Grid Size')
 data = [(r[kn], float(r[mv].replace(',', '')), r[gs]) for r in rows[hi + 1:] if len(r) > mv and r[mv].replace(',', '').replace('.', '').isdigit()]
 short = lambda n: re.sub(r'\(.*', '', n).replace('void ', '').replace('rb::', '')[:60]
-# one forward = from an enc_gather<true> (stem of fnet) to the next one that follows an upsample kernel
-starts = [i for i, d in enumerate(data) if 'enc_gather_img8' in d[0] or 'enc_gather_kernel<(bool)1>' in d[0] or 'enc_gather_kernel<1>' in short(d[0])]
+# one forward = from the stem input kernel of fnet to the next one that follows an upsample kernel
+starts = [i for i, d in enumerate(data) if 'enc_stem_s2d' in d[0] or 'enc_gather_img8' in d[0]]  # stem of fnet / cnet (r01: the gather)
 ups = [i for i, d in enumerate(data) if 'upsample_convex' in d[0] or 'upflow8' in d[0]]
 fw = None
 for u in ups:
