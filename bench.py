@@ -11,7 +11,9 @@ upsampling) over the batch.
   e2e    : pairs/s through the public API (networks.RAFT.RAFT.forward) with PINNED HOST frames:
            H2D of both frames and D2H of the flow inside the timed region, every step
   roofline        : the update-block convolutions (dominant: ~97% of hot-path FLOPs), tensor bound
-  roofline_lookup : the correlation-lookup kernel (the metric's namesake), HBM bound
+  roofline_lookup : the correlation-lookup kernel (the metric's namesake), HBM bound (B=1 cold / L2-warm, B=8)
+  roofline_corr   : rb_corr_build (volume + pooled levels), HBM side and tensor side
+  other_configs   : BASELINE configs 3-5, batch-sharded over the launched GPUs, NCCL all_gather inside the e2e span
   cpu_baseline    : the CPU oracle (torch fp32 restatement of the reference; TF is not installable)
                     timed on the host cores of the same box
 
@@ -370,8 +372,8 @@ def main():
             "note": "algorithmic fp32-equivalent FLOPs; each product costs 3 fp16 MMAs (hi/lo split), so frac <= 1/3 by design",
             "us_per_launch_group": t_upd * 1e6}
     roof_l = {"kernel": "corr_lookup_kernel<4,split>", "bound": "hbm", "achieved": look_bytes / t_look / 1e9,
-              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": 38.10e6 * B,
-              "traffic_note": "ncu --set full (profiles/r01_lookup_ncu_full.txt): dram read 38.05 MB + write 0.05 MB per cold launch (TMA boxes of 16 columns: whole 64-byte rows)",
+              "peak": pk["hbm"], "unit": "GB/s", "frac": look_bytes / t_look / 1e9 / pk["hbm"], "traffic": 35.45e6 * B,
+              "traffic_note": "ncu --set full (profiles/r02_lookup_ncu_full.txt): dram read 35.41 MB + write 0.04 MB per cold launch (TMA boxes of 16 columns x 10 rows: whole 64-byte granules)",
               "peak_source": pk["src"], "us_per_launch": t_look * 1e6,
               "l2_warm": {"us_per_launch": t_look_warm * 1e6, "achieved": look_bytes / t_look_warm / 1e9,
                           "note": "same launch without the L2 flush: at B=1 the ~25 MB of patches around the current flow stay L2-resident between iterations"}}
@@ -386,6 +388,8 @@ def main():
         t8 = ev_time(lambda: capi.check(lib.rb_update_lookup(s, capi.ptr(ws8), capi.ptr(pyr8), capi.ptr(c8), B8, h, w, capi.stream())))
         roof_l["batch8"] = {"us_per_launch": t8 * 1e6, "achieved": B8 * h * w * LOOKUP_BYTES_PER_PX / t8 / 1e9,
                             "frac": B8 * h * w * LOOKUP_BYTES_PER_PX / t8 / 1e9 / pk["hbm"],
+                            "traffic": 340.6e6,
+                            "traffic_note": "ncu --set full (profiles/r02_lookup_ncu_full.txt): dram read 285.9 MB + write 54.6 MB in 67.0 us = 5.08 TB/s = 0.77 of the copy peak on REAL traffic (64-byte DRAM granules around 40-44-byte row segments)",
                             "note": "B=8 x 440x1024 grid, N(0,1) pyramid (2.1 GB), coords = grid + U(-8,8), L2 flushed"}
         del pyr8, ws8
     except Exception as e:  # noqa: BLE001 -- an extra, never fail the bench line for it
@@ -401,7 +405,9 @@ def main():
     corr_flops = 2.0 * B * N1 * lvl_elems * eng.fdim
     roof_c = {"kernel": "rb_corr_build: conv_tc_kernel x4 (volume + 3 pooled levels by linearity) + split/pool passes",
               "bound": "hbm", "achieved": corr_bytes / t_corr / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-              "frac": corr_bytes / t_corr / 1e9 / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+              "frac": corr_bytes / t_corr / 1e9 / pk["hbm"], "traffic": 158.6e6 * B,
+              "traffic_note": "ncu --set full (profiles/r02_corr_ncu_full.txt), level-0 GEMM: dram read 14.5 MB + write 144.1 MB inside the kernel (the rest of the 198 MB it stores is still in L2 when it ends)",
+              "peak_source": pk["src"],
               "us_per_launch_group": t_corr * 1e6, "algorithmic_bytes": corr_bytes,
               "tensor": {"achieved": corr_flops / t_corr / 1e12, "unit": "TFLOP/s (fp32-equivalent; 3 fp16 MMAs per product)",
                          "frac": corr_flops / t_corr / 1e12 / pk["tf"]}}

@@ -574,7 +574,7 @@ inline int launch_conv(const ConvParams& p, cudaStream_t s) {
 
 __device__ __forceinline__ long long gtime_ns() {
   long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");  // "memory": keeps the read on its side of barriers
   return t;
 }
 inline int level_dim(int d, int level) { return d >> level; }
