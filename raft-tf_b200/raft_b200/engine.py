@@ -49,6 +49,7 @@ class RaftEngine:
         self._shape = None
         self._graph = None
         self._enc_stream = None   # forked stream of the context encoder (encode())
+        self._capture_stream = None  # CUDA-graph capture stream on this engine's device (run())
         self._cnet_pending = False
         self._range_checked = False  # first forward of this weight set: fp16-range check of the split path's inputs
 
@@ -185,7 +186,12 @@ class RaftEngine:
             body()  # warm-up: function attributes, tensor-map cache
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # torch.cuda.graph's default capture stream is a process-wide singleton on whichever device used it first, and
+            # entering it switches the current device to THAT device: an engine on another device of the same process
+            # would record its kernels there (illegal address at replay).  Capture on a stream of this engine's device.
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.graph(g, stream=self._capture_stream):
                 body()
             self._graph = g
         self._graph.replay()
