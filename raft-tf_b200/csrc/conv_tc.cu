@@ -108,6 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
   const int krank = splitk ? (int)cluster_ctarank() : 0;
+  bool cl_arrived = false;  // split-K: this thread has arrived on the closing cluster barrier
   const int first = (PAIR || splitk) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
   const int stride = (PAIR || splitk) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
@@ -329,6 +330,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const float2 t = red_buf[r];
                 v[0] += t.x;
                 v[1] += t.y;
+                cluster_arrive();  // "consumed": the closing cluster barrier completes while this warp still stores
+                cl_arrived = true;
               }
             }
           }
@@ -368,6 +371,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
+  if (splitk) {
+    // Closing cluster barrier: CTA 0 must not exit while CTA 1 may still write its shared memory.  That already follows
+    // from the data flow (CTA 0 waited for the partial sums); the barrier makes it provable (compute-sanitizer racecheck).
+    // CTA 0's epilogue lanes arrived when they consumed the sums, so by now the barrier has completed and the wait is free.
+    if (!cl_arrived) cluster_arrive();
+    cluster_wait();
+  }
   if (dbg && threadIdx.x == 0) dbg[7] = gtime_ns();
   if (warp == 1) {
     tc_fence_after();
