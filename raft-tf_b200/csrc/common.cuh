@@ -115,6 +115,7 @@ struct ConvParams {
   int stat_strips;    // stored values, [B][strips][2][cout] (strip = 4 * tile-in-image + lane quarter); encoder.cu
   int stash;      // 1: single-tile CTAs park the gate epilogues' fp32 operands in spare TMEM columns during the MMA loop
   int split_k;    // 1: K summed as (first half of the chunks) + (second half) (conv_tc.cu; cout <= 2, EPI_DELTA) ...
+  int split_close;    // launcher: closing cluster barrier of the split-K pair (RAFT_B200_SPLITK_CLOSING_BARRIER, sanitizer runs)
   int split_cluster;  // ... set by the launcher: the halves run on the two CTAs of a cluster (one wave of pairs, batch 1)
   int cta_limit;  // > 0: at most this many persistent CTAs (a conv that runs beside another one on a forked stream)
   int whatif;  // timing experiments only (fused kernel): 64 no global stores, 128 no global loads in the wide epilogue

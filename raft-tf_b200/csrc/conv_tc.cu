@@ -108,7 +108,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
   const int krank = splitk ? (int)cluster_ctarank() : 0;
-  bool cl_arrived = false;  // split-K: this thread has arrived on the closing cluster barrier
   const int first = (PAIR || splitk) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
   const int stride = (PAIR || splitk) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
@@ -330,8 +329,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const float2 t = red_buf[r];
                 v[0] += t.x;
                 v[1] += t.y;
-                cluster_arrive();  // "consumed": the closing cluster barrier completes while this warp still stores
-                cl_arrived = true;
               }
             }
           }
@@ -371,13 +368,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers
-  if (splitk) {
-    // Closing cluster barrier: CTA 0 must not exit while CTA 1 may still write its shared memory.  That already follows
-    // from the data flow (CTA 0 waited for the partial sums); the barrier makes it provable (compute-sanitizer racecheck).
-    // CTA 0's epilogue lanes arrived when they consumed the sums, so by now the barrier has completed and the wait is free.
-    if (!cl_arrived) cluster_arrive();
-    cluster_wait();
-  }
+  // Split-K: CTA 0 cannot exit before CTA 1's partial sums have landed in its shared memory -- it waited for them
+  // (mbarrier, release.cluster / acquire.cluster) -- so no closing cluster barrier is needed.  compute-sanitizer's racecheck
+  // cannot see that ("block that might have already exited"); p.split_close adds the barrier it wants (0 hazards with it,
+  // +1 us per update step: profiles/r02_notes.md).
+  if (splitk && p.split_close) cluster_sync_all();
   if (dbg && threadIdx.x == 0) dbg[7] = gtime_ns();
   if (warp == 1) {
     tc_fence_after();
@@ -545,6 +540,8 @@ static int launch_cfg(const ConvParams& p_in, TileGeom g, const CUtensorMap* map
   if (p.split_k && !(BLOCK_N == 16 && !PAIR && p.cout <= 2 && p.epi == EPI_DELTA && !p.w_per_batch && conv_chunks(p) % 2 == 0))
     p.split_k = 0;
   static const bool no_cluster = getenv("RAFT_B200_NO_SPLITK_CLUSTER") != nullptr;  // test knob: same sums on one CTA
+  static const bool close_barrier = getenv("RAFT_B200_SPLITK_CLOSING_BARRIER") != nullptr;  // for compute-sanitizer runs
+  p.split_close = close_barrier ? 1 : 0;
   p.split_cluster = (p.split_k && 2 * g.total_tiles <= num_sms && p.cta_limit <= 0 && !no_cluster) ? 1 : 0;
   const bool cluster2 = PAIR || p.split_cluster;
   cudaLaunchConfig_t cfg;
