@@ -96,6 +96,12 @@ int rb_conv2d_workspace_bytes(int B, int h, int w, int cin, int cout, int kh, in
 int rb_conv2d(const float* x, const float* W_host, const float* b_host, float* y, int B, int h, int w,
               int cin, int cout, int kh, int kw, int relu, void* workspace, size_t workspace_bytes,
               void* stream);
+/* Same with tensorpack's `strides` argument (1 or 2; the encoders' stride-2 layers, model_utils.py:21,39,68,92):
+ * y [B, ceil(h/stride), ceil(w/stride), cout], TensorFlow 'SAME' padding (pad before = total / 2, the odd one after).
+ * The strided taps are read through TMA element strides -- no gathered copy of the input.  Same workspace query. */
+int rb_conv2d_strided(const float* x, const float* W_host, const float* b_host, float* y, int B, int h, int w,
+                      int cin, int cout, int kh, int kw, int stride, int relu, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ---- A5-A11: BasicUpdateBlock / SmallUpdateBlock  model_utils.py:110-194 ----------------------
  * Weights: rb_update_num_convs(small) convolutions in the fixed order given by

@@ -1,6 +1,6 @@
-// A14: stand-alone stride-1 'same' convolution with bias (+ReLU), i.e. the tensorpack Conv2D call every
-// hot-path layer is made of (model_utils.py:112-118,123-128,133-134,142-153,162-166,181-182), on fp32
-// NHWC tensors.  Same kernels as the fused update block: the input is split to fp16 hi/lo planes, the
+// A14: stand-alone 'same' convolution with bias (+ReLU), i.e. the tensorpack Conv2D call every hot-path layer is made
+// of (stride 1: model_utils.py:112-118,123-128,133-134,142-153,162-166,181-182; stride 2: the encoders' strided layers,
+// model_utils.py:21,39,68,92), on fp32 NHWC tensors.  Same kernels as the fused update block: the input is split to fp16 hi/lo planes, the
 // HWIO kernel is packed K-major, and the selected back end (tcgen05 or CUDA-core) runs the implicit
 // GEMM.  Used by the parity tests to exercise every filter shape / tile geometry in isolation.
 #include <string.h>
@@ -62,13 +62,29 @@ extern "C" int rb_conv2d_workspace_bytes(int B, int h, int w, int cin, int cout,
   return RB_OK;
 }
 
+// TF 'SAME': out = ceil(n / s), total pad = max((out - 1) * s + k - n, 0), before = total / 2 (the rest after)
+static inline void same_pad_tf(int n, int k, int s, int* before, int* out) {
+  const int o = (n + s - 1) / s;
+  int total = (o - 1) * s + k - n;
+  if (total < 0) total = 0;
+  *before = total / 2;
+  *out = o;
+}
+
 extern "C" int rb_conv2d(const float* x, const float* W_host, const float* b_host, float* y, int B, int h, int w,
                          int cin, int cout, int kh, int kw, int relu, void* workspace, size_t workspace_bytes,
                          void* stream) {
+  return rb_conv2d_strided(x, W_host, b_host, y, B, h, w, cin, cout, kh, kw, 1, relu, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rb_conv2d_strided(const float* x, const float* W_host, const float* b_host, float* y, int B, int h, int w,
+                                 int cin, int cout, int kh, int kw, int stride, int relu, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   RB_REQUIRE(x && W_host && y && workspace, RB_ERR_BAD_ARG, "rb_conv2d: null pointer");
   RB_REQUIRE(B > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, RB_ERR_BAD_SHAPE, "rb_conv2d: bad shape");
   RB_REQUIRE((kh & 1) && (kw & 1) && kh <= 7 && kw <= 7, RB_ERR_UNSUPPORTED,
-             "rb_conv2d: only odd kernels up to 7 (stride 1, 'same'), got %dx%d", kh, kw);
+             "rb_conv2d: only odd kernels up to 7 ('same'), got %dx%d", kh, kw);
+  RB_REQUIRE(stride == 1 || stride == 2, RB_ERR_UNSUPPORTED, "rb_conv2d: stride %d (1 and 2 are what the reference uses)", stride);
   ConvWs L = conv_ws_layout(B, h, w, cin, cout, kh, kw, workspace);
   RB_REQUIRE(workspace_bytes >= L.total, RB_ERR_WORKSPACE, "rb_conv2d: workspace has %zu bytes, need %zu", workspace_bytes,
              L.total);
@@ -99,6 +115,14 @@ extern "C" int rb_conv2d(const float* x, const float* W_host, const float* b_hos
   p.w_hi = L.w_hi; p.w_lo = L.w_lo; p.bias = L.bias;
   p.cout = cout; p.cout_pad = L.cout_pad; p.kh = kh; p.kw = kw;
   p.B = B; p.h = h; p.w = w;
+  if (stride != 1) {  // strided input view (ConvParams, common.cuh): y is [B, ceil(h/s), ceil(w/s), cout]
+    int pt, pl, oh, ow;
+    same_pad_tf(h, kh, stride, &pt, &oh);
+    same_pad_tf(w, kw, stride, &pl, &ow);
+    p.in_h = h; p.in_w = w; p.h = oh; p.w = ow;
+    p.sx = p.sy = stride;
+    p.pad_explicit = 1; p.pad_x = pl; p.pad_y = pt;
+  }
   p.epi = EPI_F32; p.act = relu ? ACT_RELU : ACT_NONE; p.scale = 1.f; p.f0 = y;
   return launch_conv(p, s);
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     "rb_bilinear_sample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rb_conv2d_workspace_bytes": (_i, [_i, _i, _i, _i, _i, _i, _i, _psz]),
     "rb_conv2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "rb_conv2d_strided": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "rb_update_num_convs": (_i, [_i]),
     "rb_update_conv_name": (C.c_char_p, [_i, _i]),
     "rb_update_conv_shape": (_i, [_i, _i, _pi, _pi, _pi, _pi]),

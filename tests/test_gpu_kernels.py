@@ -217,6 +217,42 @@ def test_conv2d(cuda, mode, case):
 
 
 @pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("case", [(2, 36, 52, 64, 96, 3), (1, 37, 51, 64, 96, 3), (2, 36, 52, 96, 128, 1), (1, 33, 47, 32, 64, 1),
+                                  (1, 40, 56, 3, 64, 7), (1, 39, 57, 3, 32, 7), (1, 9, 300, 16, 16, 3)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_stride2(cuda, mode, case):
+    """tensorpack Conv2D(strides=2, 'same') as the encoders call it (model_utils.py:21,39,68,92): TF pads before = total/2
+    (0|1 for even, 1|1 for odd sizes with k=3; 2|3 and 3|3 with k=7), taps through TMA element strides.  vs torch fp64."""
+    from raft_b200 import capi
+    B, h, w, cin, cout, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, h, w, cin, generator=g)
+    W = torch.randn(k, k, cin, cout, generator=g) * (2.0 / (k * k * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = O.conv2d(x.double(), W.double(), b.double(), 2, torch.relu)
+    lib = capi.lib
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    assert ref.shape == (B, oh, ow, cout)
+    y = torch.full((B, oh, ow, cout), float("nan"), device=cuda)
+    wsb = capi.size_query(lib.rb_conv2d_workspace_bytes, B, h, w, cin, cout, k, k)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=cuda)
+    Wn, bn = np.ascontiguousarray(W.numpy()), np.ascontiguousarray(b.numpy())
+    capi.check(lib.rb_set_math_mode(dict(_modes())[mode]))
+    try:
+        capi.check(lib.rb_conv2d_strided(capi.ptr(x.to(cuda)), Wn.ctypes.data, bn.ctypes.data, capi.ptr(y), B, h, w, cin, cout,
+                                         k, k, 2, 1, capi.ptr(ws), wsb, capi.stream()))
+        torch.cuda.synchronize()
+    finally:
+        lib.rb_set_math_mode(capi.RB_MATH_TC)
+    yc = y.cpu().double()
+    assert torch.isfinite(yc).all(), f"{int((~torch.isfinite(yc)).sum())} non-finite outputs (unwritten?)"
+    err = (yc - ref).abs().max().item()
+    assert err < 2e-5 * max(ref.abs().max().item(), 1.0), f"max abs err {err:.3e}"
+    assert lib.rb_conv2d_strided(capi.ptr(y), Wn.ctypes.data, None, capi.ptr(y), B, h, w, cin, cout, k, k, 3, 0, capi.ptr(ws), wsb,
+                                 capi.stream()) == -3  # RB_ERR_UNSUPPORTED: stride 3
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
 @pytest.mark.parametrize("small", [False, True])
 def test_update_block(cuda, mode, small):
     """BasicUpdateBlock / SmallUpdateBlock (model_utils.py:172-194): (net, mask, delta_flow)."""
