@@ -336,17 +336,18 @@ def main():
     def ev_time(fn, reps=10, flush_l2=True):
         """Device time of fn() per call: `reps` x (L2 flush; fn) replayed from one CUDA graph minus the same graph
         without fn -- event timing of eager launches would measure the host launch latency for ~5 us kernels."""
-        def build(with_fn):
+        def build(with_fn, n=reps):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                for _ in range(reps):
+                for _ in range(n):
                     if flush_l2:
                         flush.zero_()
                     if with_fn:
                         fn()
             return g
         fn(); torch.cuda.synchronize()
-        g1, g0 = build(True), build(False)
+        # baseline: the same graph without fn; without the flush that graph would be empty, so difference 2*reps against reps
+        g1, g0 = (build(True), build(False)) if flush_l2 else (build(True, 2 * reps), build(True, reps))
         def run(g):
             ts = []
             for _ in range(5):
