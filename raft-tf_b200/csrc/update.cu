@@ -83,7 +83,9 @@ static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 struct PackedLayout {
   size_t hi[P_COUNT], lo[P_COUNT], bias[P_COUNT];  // byte offsets
   int cout[P_COUNT], cout_pad[P_COUNT], kh[P_COUNT], kw[P_COUNT];
-  size_t f1_w, f1_b;  // convf1: fp32 [49*2][cout] and bias
+  size_t f1_w, f1_b;  // convf1: fp32 [49*2][cout] and bias (CUDA-core kernel)
+  size_t f1t_hi, f1t_lo, f1t_bias;  // convf1 for the tensor-core path: 7x1 conv over the 8-pixel window view, [cout_pad][7][64]
+  int f1t_cout, f1t_cout_pad;
   size_t total;
 };
 
@@ -108,6 +110,13 @@ static PackedLayout packed_layout(const Variant& v) {
   const RefConv& f = v.ref[v.convf1_ref];
   L.f1_w = off; off = align_up(off + (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float), 256);
   L.f1_b = off; off = align_up(off + (size_t)f.cout * sizeof(float), 256);
+  L.f1t_cout = f.cout; L.f1t_cout_pad = pad16(f.cout);
+  {
+    const size_t plane = (size_t)L.f1t_cout_pad * 7 * 64 * sizeof(__half);
+    L.f1t_hi = off; off = align_up(off + plane, 256);
+    L.f1t_lo = off; off = align_up(off + plane, 256);
+    L.f1t_bias = off; off = align_up(off + (size_t)L.f1t_cout_pad * sizeof(float), 256);
+  }
   L.total = off;
   return L;
 }
@@ -115,6 +124,7 @@ static PackedLayout packed_layout(const Variant& v) {
 // ---- activation workspace -------------------------------------------------------------------------
 struct Workspace {
   SplitPtr corr, c1, cf, f1, hx, qx, fh;
+  SplitPtr fl;  // flow as split planes [B][h][w + 8][8]: 3 zero pixels left, 5 right, channels 0,1 = flow (convf1's window view)
   float* H;
   float* Z;
   float* pre[4];  // things: bias + conv over the `inp` channels of zr1, q1, zr2, q2 (iteration-invariant)
@@ -141,6 +151,12 @@ static Workspace workspace_layout(const Variant& v, size_t npix, void* base) {
   W.hx = split(v.hx);
   W.qx = split(v.hx);
   W.fh = split(v.fh);
+  {  // (w + 8) <= 2 w for every admissible grid (w >= 8): 2 * npix pixels of 8 channels bound the padded flow image
+    const size_t plane = align_up(2 * npix * 8 * sizeof(__half), 1024);
+    W.fl.hi = reinterpret_cast<__half*>(b + off);
+    W.fl.lo = reinterpret_cast<__half*>(b + off + plane);
+    off += 2 * plane;
+  }
   size_t fsz = align_up(npix * (size_t)v.hidden * sizeof(float), 1024);
   W.H = reinterpret_cast<float*>(b + off); off += fsz;
   W.Z = reinterpret_cast<float*>(b + off); off += fsz;
@@ -274,6 +290,36 @@ __global__ void __launch_bounds__(COUT) flow_conv7_kernel(const float2* __restri
       qx.hi[o] = hi; qx.lo[o] = lo;
     }
   }
+}
+
+// Tensor-core convf1: the 7x7x2 conv as a 7x1 conv over a view whose pixel is a window of 8 neighbouring flow pixels x 8
+// channels = 64 contiguous fp16 (the overlapping-window view of the encoder stem, ConvParams in common.cuh): K = 7 x 64 of
+// which 98 are non-zero -- 7 k-iterations on the tensor cores instead of 12 544 FMA per pixel on the CUDA cores, whose blocks
+// cannot share an SM with a conv CTA (what-if without the CUDA-core kernel: -5 us per update step at batch 1, -48 us at 8).
+// This pass writes the padded flow image [B][h][w + 8][8] (pad pixels and channels 2..7 = 0, so no reliance on earlier
+// contents) and the [.., flow] slots of HX / QX (concat_out, model_utils.py:119).  One thread per padded pixel.
+__global__ void flow_prep_kernel(const float2* __restrict__ coords1, SplitPtr fl, SplitPtr hx, SplitPtr qx, int hx_stride,
+                                 int flow_choff, int B, int h, int w) {
+  const int Wp = w + 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * h * Wp) return;
+  const int xp = i % Wp, y = (i / Wp) % h, b = i / ((size_t)Wp * h);
+  const int x = xp - 3;
+  uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+  if (x >= 0 && x < w) {
+    const size_t pix = (size_t)(b * h + y) * w + x;
+    const float2 cc = coords1[pix];
+    __half h0, l0, h1, l1;
+    split_f32(cc.x - (float)x, h0, l0);  // flow = coords1 - coords_grid (RAFT.py:95)
+    split_f32(cc.y - (float)y, h1, l1);
+    vh.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    vl.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const size_t o = pix * hx_stride + flow_choff;
+    *reinterpret_cast<uint32_t*>(hx.hi + o) = vh.x; *reinterpret_cast<uint32_t*>(hx.lo + o) = vl.x;
+    *reinterpret_cast<uint32_t*>(qx.hi + o) = vh.x; *reinterpret_cast<uint32_t*>(qx.lo + o) = vl.x;
+  }
+  *reinterpret_cast<uint4*>(fl.hi + i * 8) = vh;
+  *reinterpret_cast<uint4*>(fl.lo + i * 8) = vl;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -552,7 +598,30 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
     const float2* c1 = reinterpret_cast<const float2*>(coords1);
 #define RB_LAUNCH_CONV7(COUT, SEG) \
     flow_conv7_kernel<COUT, SEG><<<dim3((w + SEG - 1) / SEG, h, B), COUT, 0, ss->stream>>>(c1, Wf, bf, W.f1, v.f1, W.hx, W.qx, v.hx, foff, h, w)
-    if (v.small) {
+    // default: convf1 on the tensor cores (flow_prep_kernel + 7x1 conv over the window view); RAFT_B200_CONVF1_SIMT=1, the
+    // CUDA-core math mode and the fused experiment keep the CUDA-core kernel
+    static const bool f1_simt = getenv("RAFT_B200_CONVF1_SIMT") != nullptr;
+    const bool f1_tc = !f1_simt && !fused && math_mode() == RB_MATH_TC && (foff & 1) == 0 && (v.hx & 1) == 0 && w >= 8;
+    if (f1_tc) {
+      const size_t cells = (size_t)B * h * (w + 8);
+      flow_prep_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ss->stream>>>(c1, W.fl, W.hx, W.qx, v.hx, foff, B, h, w);
+      RB_CHECK_LAUNCH("flow_prep_kernel");
+      ConvParams p;
+      memset(&p, 0, sizeof(p));
+      p.in_hi = W.fl.hi; p.in_lo = W.fl.lo;
+      p.in_stride = 8; p.in_cext = 64; p.in_w = w; p.in_h = h; p.in_rowpitch = (w + 8) * 8;
+      p.cin_pad = 64; p.kh = 7; p.kw = 1;
+      p.pad_explicit = 1; p.pad_x = 0; p.pad_y = 3;
+      p.w_hi = reinterpret_cast<const __half*>(bb + L.f1t_hi);
+      p.w_lo = reinterpret_cast<const __half*>(bb + L.f1t_lo);
+      p.bias = reinterpret_cast<const float*>(bb + L.f1t_bias);
+      p.cout = L.f1t_cout; p.cout_pad = L.f1t_cout_pad;
+      p.B = B; p.h = h; p.w = w; p.hidden = v.hidden; p.scale = 1.f;
+      set_act(p, ACT_RELU, W.f1, v.f1, 0);
+      static const int lim1 = getenv("RAFT_B200_CONVF1_CTAS") ? atoi(getenv("RAFT_B200_CONVF1_CTAS")) : -1;  // tuning knob
+      p.cta_limit = lim1 >= 0 ? lim1 : ((long)B * h * w <= 16384 ? 38 : 0);
+      if ((rc = launch_conv_dbg(p, ss->stream))) return rc;
+    } else if (v.small) {
       if (seg == 8) RB_LAUNCH_CONV7(64, 8); else if (seg == 16) RB_LAUNCH_CONV7(64, 16); else RB_LAUNCH_CONV7(64, 32);
     } else {
       if (seg == 8) RB_LAUNCH_CONV7(128, 8); else if (seg == 16) RB_LAUNCH_CONV7(128, 16); else RB_LAUNCH_CONV7(128, 32);
@@ -779,6 +848,20 @@ extern "C" int rb_update_weights_pack(int small, const float* const* W_host, con
     const RefConv& f = v.ref[v.convf1_ref];
     memcpy(host.data() + L.f1_w, W_host[v.convf1_ref], (size_t)f.kh * f.kw * f.cin * f.cout * sizeof(float));
     memcpy(host.data() + L.f1_b, b_host[v.convf1_ref], (size_t)f.cout * sizeof(float));
+    // tensor-core form: tap (ky, kx), flow channel c -> [co][ky][kx * 8 + c] (window pixel kx of 8, 8 channels per pixel)
+    RB_REQUIRE(f.kh == 7 && f.kw == 7 && f.cin == 2, RB_ERR_BAD_SHAPE, "internal: convf1 is expected to be 7x7x2");
+    __half* hi = reinterpret_cast<__half*>(host.data() + L.f1t_hi);
+    __half* lo = reinterpret_cast<__half*>(host.data() + L.f1t_lo);
+    float* bias = reinterpret_cast<float*>(host.data() + L.f1t_bias);
+    const float* Wsrc = W_host[v.convf1_ref];
+    for (int ky = 0; ky < 7; ++ky)
+      for (int kx = 0; kx < 7; ++kx)
+        for (int c = 0; c < 2; ++c)
+          for (int co = 0; co < f.cout; ++co) {
+            const size_t o = ((size_t)co * 7 + ky) * 64 + kx * 8 + c;
+            split_f32(Wsrc[((size_t)(ky * 7 + kx) * 2 + c) * f.cout + co], hi[o], lo[o]);
+          }
+    for (int co = 0; co < f.cout; ++co) bias[co] = b_host[v.convf1_ref][co];
   }
   cudaStream_t s = (cudaStream_t)stream;
   RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), L.total, cudaMemcpyHostToDevice, s));

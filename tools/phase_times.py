@@ -20,7 +20,7 @@ c1 = coords.clone()
 step = lambda: capi.check(lib.rb_update_step(s, capi.ptr(blob), capi.ptr(ws), capi.ptr(c1), None, None, B, h, w, capi.stream()))
 for _ in range(3): step()
 torch.cuda.synchronize()
-NC = 12
+NC = 13
 buf = torch.zeros(NC * 4096 * 8, dtype=torch.int64, device=dev)
 lib.rb_debug_set_buffer(capi.ptr(buf))
 g = torch.cuda.CUDAGraph()
@@ -29,7 +29,7 @@ with torch.cuda.graph(g):
 lib.rb_debug_set_buffer(None)
 g.replay(); torch.cuda.synchronize()
 t = buf.view(NC, 4096, 8).cpu().double()
-names = ["convf2(side)", "convc1", "convc2", "motion", "zr1", "q1", "zr2", "q2", "fh1", "fh2"]
+names = ["convf1(side)", "convf2(side)", "convc1", "convc2", "motion", "zr1", "q1", "zr2", "q2", "fh1", "fh2"]
 print("second step of a 2-step graph; us relative to each conv's earliest CTA start")
 t0_prev = None
 for i in range(NC):
