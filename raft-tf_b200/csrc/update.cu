@@ -619,7 +619,9 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
       p.B = B; p.h = h; p.w = w; p.hidden = v.hidden; p.scale = 1.f;
       set_act(p, ACT_RELU, W.f1, v.f1, 0);
       static const int lim1 = getenv("RAFT_B200_CONVF1_CTAS") ? atoi(getenv("RAFT_B200_CONVF1_CTAS")) : -1;  // tuning knob
-      p.cta_limit = lim1 >= 0 ? lim1 : ((long)B * h * w <= 16384 ? 38 : 0);
+      // batch 1: 28 CTAs = the 55 128-wide tiles in two full rounds (same-box sweep of both budgets, 4 iterations:
+      // 19/38: 650, 28/28: 633, 28/38: 632, 38/38: 637, 55/38: 651, 38/55: 650, 110/38: 649 us)
+      p.cta_limit = lim1 >= 0 ? lim1 : ((long)B * h * w <= 16384 ? 28 : 0);
       if ((rc = launch_conv_dbg(p, ss->stream))) return rc;
     } else if (v.small) {
       if (seg == 8) RB_LAUNCH_CONV7(64, 8); else if (seg == 16) RB_LAUNCH_CONV7(64, 16); else RB_LAUNCH_CONV7(64, 32);
