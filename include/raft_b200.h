@@ -114,6 +114,13 @@ int rb_update_conv_shape(int small, int i, int* kh, int* kw, int* cin, int* cout
 int rb_update_weights_bytes(int small, size_t* bytes);
 int rb_update_weights_pack(int small, const float* const* W_host, const float* const* b_host,
                            void* blob, size_t blob_bytes, void* stream);
+/* Host-only forms (no GPU needed): the same blob written to host memory, and where packed conv `id` lives inside it
+ * (id 0..11: convc1, convc2, convf2, motion-encoder conv, convz|r 1, convq1, convz|r 2, convq2, flow-head conv1, conv2, mask
+ * conv0, conv2; 100: the tensor-core form of convf1).  Planes are [cout_pad][kh*kw][cin_pad] fp16 (hi, lo) + fp32 bias. */
+int rb_update_weights_pack_host(int small, const float* const* W_host, const float* const* b_host, void* host_blob,
+                                size_t blob_bytes);
+int rb_update_packed_conv(int small, int id, size_t* hi_off, size_t* lo_off, size_t* bias_off, int* kh, int* kw,
+                          int* cin_pad, int* cout, int* cout_pad);
 
 /* Workspace holding the recurrent state (net), the context features (inp) and every per-iteration
  * activation.  Must be zero-filled by the caller once before first use (cudaMemset). */
@@ -195,6 +202,12 @@ int rb_encoder_weights_bytes(int small, int out_dim, size_t* bytes);
 int rb_encoder_weights_pack(int small, int norm, int out_dim, const float* const* W_host,
                             const float* const* b_host, const float* const* bn_host, void* blob,
                             size_t blob_bytes, void* stream);
+/* Host-only forms (no GPU needed), as for the update block; conv index i as in rb_encoder_conv_name.  The stem is packed
+ * as a 4x1 conv over the space-to-depth view (csrc/encoder.cu), batch norm is folded into weights and bias. */
+int rb_encoder_weights_pack_host(int small, int norm, int out_dim, const float* const* W_host, const float* const* b_host,
+                                 const float* const* bn_host, void* host_blob, size_t blob_bytes);
+int rb_encoder_packed_conv(int small, int out_dim, int i, size_t* hi_off, size_t* lo_off, size_t* bias_off, int* kh, int* kw,
+                           int* cin_pad, int* cout_pad);
 int rb_encoder_workspace_bytes(int small, int B, int H, int W, size_t* bytes);
 int rb_encoder_forward(int small, int norm, const void* weights, const float* image, float* out, int B,
                        int H, int W, int out_dim, void* workspace, size_t workspace_bytes, void* stream);

@@ -444,18 +444,40 @@ extern "C" int rb_encoder_weights_bytes(int small, int out_dim, size_t* bytes) {
   return RB_OK;
 }
 
-// bn_host[i] (NORM_BATCH only): 4*cout floats [gamma | beta | mean/EMA | variance/EMA] of the norm after conv i
-extern "C" int rb_encoder_weights_pack(int small, int norm, int out_dim, const float* const* W_host,
-                                       const float* const* b_host, const float* const* bn_host, void* blob,
-                                       size_t blob_bytes, void* stream) {
-  RB_REQUIRE(W_host && b_host && blob, RB_ERR_BAD_ARG, "rb_encoder_weights_pack: null pointer");
+// Layout of conv i inside the packed blob (byte offsets of the hi / lo / bias planes and the packed geometry).
+extern "C" int rb_encoder_packed_conv(int small, int out_dim, int i, size_t* hi_off, size_t* lo_off, size_t* bias_off, int* kh,
+                                      int* kw, int* cin_pad, int* cout_pad) {
+  std::vector<EncPacked> P;
+  size_t total;
+  enc_packed_layout(small, out_dim, P, &total);
+  RB_REQUIRE(i >= 0 && i < (int)P.size() && out_dim > 0, RB_ERR_BAD_ARG, "rb_encoder_packed_conv: index %d out of range", i);
+  if (hi_off) *hi_off = P[i].hi;
+  if (lo_off) *lo_off = P[i].lo;
+  if (bias_off) *bias_off = P[i].bias;
+  if (kh) *kh = P[i].kh;
+  if (kw) *kw = P[i].kw;
+  if (cin_pad) *cin_pad = P[i].cin_pad;
+  if (cout_pad) *cout_pad = P[i].cout_pad;
+  return RB_OK;
+}
+
+// bn_host[i] (NORM_BATCH only): 4*cout floats [gamma | beta | mean/EMA | variance/EMA] of the norm after conv i.
+// Host-only: the blob rb_encoder_weights_pack uploads, written to host memory (no GPU needed; tests/test_packing.py).
+extern "C" int rb_encoder_weights_pack_host(int small, int norm, int out_dim, const float* const* W_host,
+                                            const float* const* b_host, const float* const* bn_host, void* host_blob,
+                                            size_t blob_bytes) {
+  RB_REQUIRE(W_host && b_host && host_blob, RB_ERR_BAD_ARG, "rb_encoder_weights_pack: null pointer");
   RB_REQUIRE(norm >= 0 && norm <= 2, RB_ERR_BAD_ARG, "rb_encoder_weights_pack: norm %d", norm);
   std::vector<EncPacked> P;
   size_t total;
   enc_packed_layout(small, out_dim, P, &total);
   RB_REQUIRE(blob_bytes >= total, RB_ERR_WORKSPACE, "rb_encoder_weights_pack: blob has %zu bytes, need %zu", blob_bytes, total);
   EncDesc d = enc_desc(small);
-  std::vector<char> host(total, 0);
+  struct HostBlob {  // same interface as the std::vector<char> the loop below was written for
+    char* p;
+    char* data() { return p; }
+  } host{reinterpret_cast<char*>(host_blob)};
+  memset(host_blob, 0, total);
   for (int i = 0; i < d.n; ++i) {
     const EncConv& c = d.convs[i];
     const EncPacked& p = P[i];
@@ -487,6 +509,19 @@ extern "C" int rb_encoder_weights_pack(int small, int norm, int out_dim, const f
       bias[co] = (float)(b_host[i][co] * scale + shift);
     }
   }
+  return RB_OK;
+}
+
+extern "C" int rb_encoder_weights_pack(int small, int norm, int out_dim, const float* const* W_host,
+                                       const float* const* b_host, const float* const* bn_host, void* blob,
+                                       size_t blob_bytes, void* stream) {
+  RB_REQUIRE(blob, RB_ERR_BAD_ARG, "rb_encoder_weights_pack: null pointer");
+  size_t total = 0;
+  int rc = rb_encoder_weights_bytes(small, out_dim, &total);
+  if (rc) return rc;
+  RB_REQUIRE(blob_bytes >= total, RB_ERR_WORKSPACE, "rb_encoder_weights_pack: blob has %zu bytes, need %zu", blob_bytes, total);
+  std::vector<char> host(total, 0);
+  if ((rc = rb_encoder_weights_pack_host(small, norm, out_dim, W_host, b_host, bn_host, host.data(), total))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), total, cudaMemcpyHostToDevice, s));
   RB_CHECK_CUDA(cudaStreamSynchronize(s));

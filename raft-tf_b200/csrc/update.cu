@@ -811,16 +811,41 @@ extern "C" int rb_update_weights_bytes(int small, size_t* bytes) {
   return RB_OK;
 }
 
-extern "C" int rb_update_weights_pack(int small, const float* const* W_host, const float* const* b_host,
-                                      void* blob, size_t blob_bytes, void* stream) {
+// Layout of packed conv `id` (0 .. 11 in the order convc1, convc2, convf2, motion encoder conv, convz|r 1, convq1, convz|r 2,
+// convq2, flow-head conv1, conv2, mask conv0, conv2; 100 = the tensor-core form of convf1, [cout_pad][7][64]) inside the blob.
+// cout == 0: the variant does not have this conv.
+extern "C" int rb_update_packed_conv(int small, int id, size_t* hi_off, size_t* lo_off, size_t* bias_off, int* kh, int* kw,
+                                     int* cin_pad, int* cout, int* cout_pad) {
   const Variant& v = variant(small);
   const PackedLayout L = packed_layout(v);
-  RB_REQUIRE(W_host && b_host && blob, RB_ERR_BAD_ARG, "rb_update_weights_pack: null pointer");
+  RB_REQUIRE((id >= 0 && id < P_COUNT) || id == 100, RB_ERR_BAD_ARG, "rb_update_packed_conv: id %d", id);
+  const bool f1 = id == 100;
+  if (hi_off) *hi_off = f1 ? L.f1t_hi : L.hi[id];
+  if (lo_off) *lo_off = f1 ? L.f1t_lo : L.lo[id];
+  if (bias_off) *bias_off = f1 ? L.f1t_bias : L.bias[id];
+  if (kh) *kh = f1 ? 7 : L.kh[id];
+  if (kw) *kw = f1 ? 1 : L.kw[id];
+  if (cin_pad) *cin_pad = f1 ? 64 : v.pk[id].cin_pad;
+  if (cout) *cout = f1 ? L.f1t_cout : L.cout[id];
+  if (cout_pad) *cout_pad = f1 ? L.f1t_cout_pad : L.cout_pad[id];
+  return RB_OK;
+}
+
+// Host-only: the blob rb_update_weights_pack uploads, written to host memory (no GPU needed; tests/test_packing.py).
+extern "C" int rb_update_weights_pack_host(int small, const float* const* W_host, const float* const* b_host, void* host_blob,
+                                           size_t blob_bytes) {
+  const Variant& v = variant(small);
+  const PackedLayout L = packed_layout(v);
+  RB_REQUIRE(W_host && b_host && host_blob, RB_ERR_BAD_ARG, "rb_update_weights_pack: null pointer");
   RB_REQUIRE(blob_bytes >= L.total, RB_ERR_WORKSPACE, "rb_update_weights_pack: blob has %zu bytes, need %zu",
              blob_bytes, L.total);
   for (int i = 0; i < v.nref; ++i)
     RB_REQUIRE(W_host[i] && b_host[i], RB_ERR_BAD_ARG, "rb_update_weights_pack: missing weights for %s", v.ref[i].name);
-  std::vector<char> host(L.total, 0);
+  struct HostBlob {
+    char* p;
+    char* data() { return p; }
+  } host{reinterpret_cast<char*>(host_blob)};
+  memset(host_blob, 0, L.total);
   for (int id = 0; id < P_COUNT; ++id) {
     const PackedConv& pc = v.pk[id];
     if (pc.src0 < 0) continue;
@@ -865,8 +890,19 @@ extern "C" int rb_update_weights_pack(int small, const float* const* W_host, con
           }
     for (int co = 0; co < f.cout; ++co) bias[co] = b_host[v.convf1_ref][co];
   }
+  return RB_OK;
+}
+
+extern "C" int rb_update_weights_pack(int small, const float* const* W_host, const float* const* b_host,
+                                      void* blob, size_t blob_bytes, void* stream) {
+  RB_REQUIRE(blob, RB_ERR_BAD_ARG, "rb_update_weights_pack: null pointer");
+  const size_t total = packed_layout(variant(small)).total;
+  RB_REQUIRE(blob_bytes >= total, RB_ERR_WORKSPACE, "rb_update_weights_pack: blob has %zu bytes, need %zu", blob_bytes, total);
+  std::vector<char> host(total, 0);
+  int rc = rb_update_weights_pack_host(small, W_host, b_host, host.data(), total);
+  if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), L.total, cudaMemcpyHostToDevice, s));
+  RB_CHECK_CUDA(cudaMemcpyAsync(blob, host.data(), total, cudaMemcpyHostToDevice, s));
   RB_CHECK_CUDA(cudaStreamSynchronize(s));  // `host` dies at return; packing is an init-time call
   return RB_OK;
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "rb_update_conv_shape": (_i, [_i, _i, _pi, _pi, _pi, _pi]),
     "rb_update_weights_bytes": (_i, [_i, _psz]),
     "rb_update_weights_pack": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _vp]),
+    "rb_update_weights_pack_host": (_i, [_i, C.POINTER(_vp), C.POINTER(_vp), _vp, _sz]),
+    "rb_update_packed_conv": (_i, [_i, _i, _psz, _psz, _psz, _pi, _pi, _pi, _pi, _pi]),
     "rb_update_workspace_bytes": (_i, [_i, _i, _i, _i, _psz]),
     "rb_update_set_state": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rb_update_set_state_cnet": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "rb_encoder_conv_shape": (_i, [_i, _i, _i, _pi, _pi, _pi, _pi]),
     "rb_encoder_weights_bytes": (_i, [_i, _i, _psz]),
     "rb_encoder_weights_pack": (_i, [_i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _sz, _vp]),
+    "rb_encoder_weights_pack_host": (_i, [_i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _sz]),
+    "rb_encoder_packed_conv": (_i, [_i, _i, _i, _psz, _psz, _psz, _pi, _pi, _pi, _pi]),
     "rb_encoder_workspace_bytes": (_i, [_i, _i, _i, _i, _psz]),
     "rb_encoder_forward": (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
