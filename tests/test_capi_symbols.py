@@ -36,3 +36,11 @@ def test_host_only_queries():
     assert lib.rb_corr_pyramid_bytes(1, 4, 4, ctypes.byref(out)) == -1
     assert b"too small" in lib.rb_last_error()
     assert lib.rb_set_math_mode(7) == -2
+    # argument checks come before any CUDA call: unsupported stride / even kernel -> RB_ERR_UNSUPPORTED on a CPU-only box
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.rb_conv2d_strided(p, p, None, p, 1, 8, 8, 4, 4, 3, 3, 3, 0, p, 64, None) == -3
+    assert b"stride" in lib.rb_last_error()
+    assert lib.rb_conv2d_strided(p, p, None, p, 1, 8, 8, 4, 4, 2, 2, 1, 0, p, 64, None) == -3
+    assert lib.rb_update_packed_conv(0, 12, None, None, None, None, None, None, None, None) == -2
+
