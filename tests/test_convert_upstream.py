@@ -189,3 +189,114 @@ def test_update_block_matches_upstream_module(converted):
     on, om, od = O.basic_update_block(_nhwc(net), _nhwc(inp), _nhwc(corr), _nhwc(flow), p)
     for a, b in ((on, rn), (om, rm), (od, rd)):
         assert (a - _nhwc(b)).abs().max().item() < 1e-9 * max(b.abs().max().item(), 1.0)
+
+
+# ---- raft-small: BottleneckBlock encoders (fnet: instance norm, cnet: no norm), ConvGRU update block --------------------
+class BottleneckBlock(nn.Module):
+    def __init__(self, cin, planes, norm, stride):
+        super().__init__()
+        q = planes // 4
+        self.conv1 = nn.Conv2d(cin, q, 1)
+        self.conv2 = nn.Conv2d(q, q, 3, padding=1, stride=stride)
+        self.conv3 = nn.Conv2d(q, planes, 1)
+        self.norm1, self.norm2, self.norm3 = _norm(norm, q), _norm(norm, q), _norm(norm, planes)
+        self.downsample = None
+        if stride != 1:
+            self.norm4 = _norm(norm, planes)
+            self.downsample = nn.Sequential(nn.Conv2d(cin, planes, 1, stride=stride), self.norm4)
+
+    def forward(self, x):
+        y = F.relu(self.norm1(self.conv1(x)))
+        y = F.relu(self.norm2(self.conv2(y)))
+        y = F.relu(self.norm3(self.conv3(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return F.relu(x + y)
+
+
+class SmallEncoder(nn.Module):
+    def __init__(self, out_dim, norm):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 32, 7, stride=2, padding=3)
+        self.norm1 = _norm(norm, 32)
+        self.layer1 = nn.Sequential(BottleneckBlock(32, 32, norm, 1), BottleneckBlock(32, 32, norm, 1))
+        self.layer2 = nn.Sequential(BottleneckBlock(32, 64, norm, 2), BottleneckBlock(64, 64, norm, 1))
+        self.layer3 = nn.Sequential(BottleneckBlock(64, 96, norm, 2), BottleneckBlock(96, 96, norm, 1))
+        self.conv2 = nn.Conv2d(96, out_dim, 1)
+
+    def forward(self, x):
+        x = F.relu(self.norm1(self.conv1(x)))
+        return self.conv2(self.layer3(self.layer2(self.layer1(x))))
+
+
+class SmallUpdateBlock(nn.Module):
+    def __init__(self):
+        super().__init__()
+        enc = nn.Module()
+        enc.convc1 = nn.Conv2d(4 * 49, 96, 1)
+        enc.convf1 = nn.Conv2d(2, 64, 7, padding=3)
+        enc.convf2 = nn.Conv2d(64, 32, 3, padding=1)
+        enc.conv = nn.Conv2d(128, 80, 3, padding=1)
+        self.encoder = enc
+        gru = nn.Module()
+        for g in "zrq":
+            setattr(gru, "conv" + g, nn.Conv2d(96 + 82 + 64, 96, 3, padding=1))
+        self.gru = gru
+        fh = nn.Module()
+        fh.conv1 = nn.Conv2d(96, 128, 3, padding=1)
+        fh.conv2 = nn.Conv2d(128, 2, 3, padding=1)
+        self.flow_head = fh
+
+    def forward(self, net, inp, corr, flow):
+        e, g, f = self.encoder, self.gru, self.flow_head
+        cor = F.relu(e.convc1(corr))
+        flo = F.relu(e.convf2(F.relu(e.convf1(flow))))
+        x = torch.cat([inp, F.relu(e.conv(torch.cat([cor, flo], 1))), flow], 1)
+        hx = torch.cat([net, x], 1)
+        z, r = torch.sigmoid(g.convz(hx)), torch.sigmoid(g.convr(hx))
+        q = torch.tanh(g.convq(torch.cat([r * net, x], 1)))
+        net = (1 - z) * net + z * q
+        return net, f.conv2(F.relu(f.conv1(net)))
+
+
+class UpstreamSmall(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fnet = SmallEncoder(128, "instance")
+        self.cnet = SmallEncoder(96 + 64, "none")
+        self.update_block = SmallUpdateBlock()
+
+
+@pytest.fixture(scope="module")
+def converted_small(tmp_path_factory):
+    torch.manual_seed(4321)
+    m = UpstreamSmall().eval()
+    d = tmp_path_factory.mktemp("ckpt_small")
+    pth, npz = str(d / "raft-small.pth"), str(d / "raft-small.npz")
+    torch.save({"module." + k: v for k, v in m.state_dict().items()}, pth)
+    assert convert.main([pth, npz]) == 0
+    return m.double().eval(), {k: torch.from_numpy(v).double() for k, v in load_npz(npz).items()}
+
+
+def test_small_model_matches_upstream_modules(converted_small):
+    m, p = converted_small
+    from raft_b200 import synth
+    assert set(p) == set(synth.make_weights(True))  # exactly the reference's variable names for raft-small
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(1, 3, 73, 57, generator=g, dtype=torch.float64) * 2 - 1  # 73 -> 37 -> 19 -> 10, 57 -> 29 -> 15 -> 8
+    with torch.no_grad():
+        for name, norm in (("fnet", "instance"), ("cnet", "none")):
+            ref = _nhwc(getattr(m, name)(x))
+            out = O.small_encoder(_nhwc(x), p, name, norm)
+            assert out.shape == ref.shape and (out - ref).abs().max().item() < 1e-9 * max(ref.abs().max().item(), 1.0), name
+        B, h, w = 1, 8, 11
+        net = torch.tanh(torch.randn(B, 96, h, w, generator=g, dtype=torch.float64))
+        inp = torch.relu(torch.randn(B, 64, h, w, generator=g, dtype=torch.float64))
+        corr = torch.randn(B, 196, h, w, generator=g, dtype=torch.float64)
+        flow = torch.randn(B, 2, h, w, generator=g, dtype=torch.float64) * 3
+        rn, rd = m.update_block(net, inp, corr, flow)
+    on, om, od = O.small_update_block(_nhwc(net), _nhwc(inp), _nhwc(corr), _nhwc(flow), p)
+    assert om is None
+    for a, b in ((on, rn), (od, rd)):
+        assert (a - _nhwc(b)).abs().max().item() < 1e-9 * max(b.abs().max().item(), 1.0)
+
