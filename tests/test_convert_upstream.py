@@ -300,3 +300,59 @@ def test_small_model_matches_upstream_modules(converted_small):
     for a, b in ((on, rn), (od, rd)):
         assert (a - _nhwc(b)).abs().max().item() < 1e-9 * max(b.abs().max().item(), 1.0)
 
+
+
+# ---- correlation pyramid + lookup against an upstream-style CorrBlock on torch.grid_sample -------------------------------
+def _upstream_corr_lookup(fmap1, fmap2, coords, radius, levels=4):
+    """All-pairs volume / sqrt(C), 2x2 average pyramid over the target axes, (2r+1)^2 bilinear taps per level around
+    coords / 2^i with the FIRST window axis added to x (the published implementation stacks meshgrid(dy, dx) onto (x, y)
+    coordinates); zero outside.  fmap NCHW, coords [B,2,H,W] (x, y) -> [B, levels*(2r+1)^2, H, W]."""
+    B, C, H, W = fmap1.shape
+    corr = torch.matmul(fmap1.view(B, C, H * W).transpose(1, 2), fmap2.view(B, C, H * W)) / C ** 0.5
+    corr = corr.view(B * H * W, 1, H, W)
+    pyr = [corr]
+    for _ in range(levels - 1):
+        corr = F.avg_pool2d(corr, 2, stride=2)
+        pyr.append(corr)
+    c = coords.permute(0, 2, 3, 1).reshape(B * H * W, 1, 1, 2)
+    d = torch.linspace(-radius, radius, 2 * radius + 1, dtype=coords.dtype)
+    delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1)  # delta[i, j] = (d[i], d[j]) added to (x, y)
+    out = []
+    for i, vol in enumerate(pyr):
+        xy = c / 2 ** i + delta[None]
+        hl, wl = vol.shape[-2:]
+        grid = torch.stack([2 * xy[..., 0] / (wl - 1) - 1, 2 * xy[..., 1] / (hl - 1) - 1], dim=-1)
+        s = F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+        out.append(s.view(B, H, W, -1))
+    return torch.cat(out, dim=-1)
+
+
+@pytest.mark.parametrize("radius", [4, 3])
+def test_pyramid_lookup_matches_grid_sample_corr_block(radius):
+    """Volume scaling, VALID 2x2 pooling, coords / 2^i, x-major window and level order of the oracle (= the reference's
+    GetCorrPyramid / SampleCorr) against torch.grid_sample, on the taps that lie strictly inside their level (at and beyond
+    the border the reference's truncating / clamping sampler deliberately differs from zero padding: utils.py:54-89)."""
+    g = torch.Generator().manual_seed(21)
+    B, C, H, W = 1, 16, 40, 72
+    f1 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    f2 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    coords = torch.stack([xs, ys], 0)[None] + (torch.rand(B, 2, H, W, generator=g, dtype=torch.float64) * 6 - 3)
+    ref = _upstream_corr_lookup(f1, f2, coords, radius)
+    pyr = O.get_corr_pyramid(_nhwc(f1), _nhwc(f2))
+    out = O.sample_corr(pyr, _nhwc(coords), radius=radius)
+    assert out.shape == ref.shape == (B, H, W, 4 * (2 * radius + 1) ** 2)
+    n = (2 * radius + 1) ** 2
+    d = torch.linspace(-radius, radius, 2 * radius + 1, dtype=torch.float64)
+    dx, dy = d[:, None].expand(-1, 2 * radius + 1).reshape(-1), d[None, :].expand(2 * radius + 1, -1).reshape(-1)
+    checked = 0
+    for i in range(4):
+        hl, wl = H >> i, W >> i
+        x = _nhwc(coords)[..., 0:1] / 2 ** i + dx
+        y = _nhwc(coords)[..., 1:2] / 2 ** i + dy
+        inside = (x > 0) & (x < wl - 1) & (y > 0) & (y < hl - 1)
+        a, b = out[..., i * n:(i + 1) * n][inside], ref[..., i * n:(i + 1) * n][inside]
+        assert inside.float().mean().item() > (0.5 if i < 3 else 0.1), i
+        assert (a - b).abs().max().item() < 1e-10 * max(b.abs().max().item(), 1.0), f"level {i}"
+        checked += int(inside.sum())
+    assert checked > 100000
