@@ -356,3 +356,30 @@ def test_pyramid_lookup_matches_grid_sample_corr_block(radius):
         assert (a - b).abs().max().item() < 1e-10 * max(b.abs().max().item(), 1.0), f"level {i}"
         checked += int(inside.sum())
     assert checked > 100000
+
+
+# ---- the output edge: convex upsampling and upflow8 against their torch forms ---------------------------------------------
+def test_convex_upsampling_matches_unfold_form():
+    """RAFT.upsample_flow (RAFT.py:118-134: softmax over the 9 taps, tf.extract_image_patches of 8*flow, reshape (9, 2))
+    against the published torch form (softmax over dim 2 of mask.view(N,1,9,8,8,H,W), F.unfold of 8*flow): pins the
+    (ky, kx, c) depth order of extract_image_patches and the (9, 8, 8) layout of the 576 mask channels independently."""
+    g = torch.Generator().manual_seed(31)
+    N, H, W = 2, 5, 7
+    flow = torch.randn(N, 2, H, W, generator=g, dtype=torch.float64) * 3
+    mask = torch.randn(N, 576, H, W, generator=g, dtype=torch.float64)
+    m = torch.softmax(mask.view(N, 1, 9, 8, 8, H, W), dim=2)
+    up = F.unfold(8 * flow, [3, 3], padding=1).view(N, 2, 9, 1, 1, H, W)
+    ref = torch.sum(m * up, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(N, 2, 8 * H, 8 * W)
+    out = O.upsample_flow(_nhwc(flow), _nhwc(mask))
+    assert out.shape == (N, 8 * H, 8 * W, 2)
+    assert (out - _nhwc(ref)).abs().max().item() < 1e-12 * max(ref.abs().max().item(), 1.0)
+
+
+def test_upflow8_is_align_corners_resize_without_the_factor_8():
+    """utils.py:105-111: tf.image.resize_bilinear(align_corners=True) -- and, unlike upstream, NOT multiplied by 8."""
+    g = torch.Generator().manual_seed(32)
+    flow = torch.randn(2, 2, 6, 9, generator=g, dtype=torch.float64)
+    ref = F.interpolate(flow, size=(48, 72), mode="bilinear", align_corners=True)
+    out = O.upflow8(_nhwc(flow))
+    # the oracle forms the source coordinates in float32 like TF's kernel (out_idx * float((in-1)/(out-1))): ~1e-6 of a pixel
+    assert (out - _nhwc(ref)).abs().max().item() < 1e-5
