@@ -3,7 +3,9 @@ published architecture, their genuine ``state_dict()`` keys ('module.' prefix of
 the norm of a strided block registered twice as ``norm3`` and ``downsample.1``) saved with ``torch.save`` -- goes through the
 converter CLI into the reference's ``.npz`` naming, and the oracle (the restatement of the reference's TF graph) must then
 compute what the torch modules compute.  That pins the key mapping, OIHW -> HWIO, the BatchNorm statistics and, as a side
-effect, the oracle's block structure against an independent implementation.
+effect, the oracle's block structure against an independent implementation.  Further down: the oracle's correlation pyramid
++ lookup against an upstream-style CorrBlock on torch.grid_sample, convex upsampling against the F.unfold form, upflow8 against
+F.interpolate(align_corners=True) -- the TF ops whose semantics the numpy shim (oracle/ref_shim) had to assume.
 
 Sizes: every stride-2 conv sees an ODD extent, where PyTorch's symmetric ``padding = k // 2`` and TensorFlow's ``SAME``
 (pad before = total / 2) coincide; on even extents the TF port samples one pixel later than upstream by construction."""
