@@ -7,6 +7,7 @@
 //   C1   [256]    relu(convc1)                                   (things only)
 //   CF   [cf]     [cor | flo]      = input of encoder/conv       (model_utils.py:117,127)
 //   F1   [f1]     relu(convf1)
+//   FL   [8]      the flow as a zero-padded image [B][h][w+8] (channels 0,1): operand of convf1's 8-pixel window view
 //   HX   [hx]     [h | inp | motion_out | flow | 0-pad] = GRU z/r input (cat_hx, :141,150,160)
 //   QX   [hx]     [r*h | inp | motion_out | flow | 0-pad] = GRU q input (:144,153,165)
 //   FH   [fh]     relu(flow_head/conv1); reused for relu(mask/0)
@@ -235,7 +236,8 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
   if (i < n) dst[i] = src[i];
 }
 
-// encoder/convf1: 7x7 conv over the 2-channel flow + ReLU (model_utils.py:114,124), CUDA cores
+// encoder/convf1: 7x7 conv over the 2-channel flow + ReLU (model_utils.py:114,124), CUDA-core form: the cross-check back end
+// (RB_MATH_SIMT) and RAFT_B200_CONVF1_SIMT=1; the default is the tensor-core form (flow_prep_kernel below + conv_tc)
 // (K = 98 is no tensor-core shape).  flow = coords1 - coords_grid (RAFT.py:95) is formed while
 // staging; SAME padding zero-pads the FLOW.  One thread per output channel, SEG-pixel row segment
 // per block (SEG = 16 at batch 1: 440 blocks instead of 220 -- the kernel is latency-bound, and with the convf2 that
@@ -590,7 +592,7 @@ static int update_step(const Variant& v, const void* blob, void* wsp, float* coo
   if ((rc = side_stream(&ss))) return rc;
   RB_CHECK_CUDA(cudaEventRecord(ss->fork, s));
   RB_CHECK_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-  {  // flow branch (side stream): convf1 (7x7, CUDA cores) -> convf2
+  {  // flow branch (side stream): convf1 (7x7) -> convf2
     static const int seg_env = getenv("RAFT_B200_CONV7_SEG") ? atoi(getenv("RAFT_B200_CONV7_SEG")) : 0;  // tuning knob
     const int seg = seg_env ? seg_env : ((long)B * h * w <= 16384 ? 16 : 32);  // same-box A/B at 55x128: 792 / 772 / 781 us per 4 iterations for 32 / 16 / 8
     const float* Wf = reinterpret_cast<const float*>(bb + L.f1_w);
